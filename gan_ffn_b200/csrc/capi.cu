@@ -1,0 +1,213 @@
+// C ABI (include/ganffn.h) over the kernel files, plus the library state and the GEMM engine
+// dispatcher.
+#include <stdarg.h>
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace ganffn {
+
+unsigned long long g_launches = 0;
+int g_gemm_engine = GANFFN_GEMM_AUTO;
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- GEMM engine dispatch -------------------------------------------------------------------------------
+// AUTO: tcgen05 3xTF32 tiles when the problem has tensor-sized extents, else the FFMA engine.
+static bool use_tc(bool transA, bool b_is_nk, int lda, int ldb, int ldc, int M, int N, int K, const void* A,
+                   const void* B) {
+  if (g_gemm_engine == GANFFN_GEMM_SIMT) return false;
+  return gemm_tc_supported(transA, b_is_nk, lda, ldb, ldc, M, N, K, A, B);
+}
+
+int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
+         int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st) {
+  if (use_tc(transA, b_is_nk, lda, ldb, ldc, M, N, K, A, B))
+    return gemm_tc(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
+  return gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
+}
+
+int64_t gemm_scratch_floats(int M, int N, int K) {
+  return std::max(gemm_simt_scratch_floats(M, N, K), gemm_tc_scratch_floats(M, N, K));
+}
+
+}  // namespace ganffn
+
+using namespace ganffn;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int ganffn_version(void) { return 100; }
+const char* ganffn_last_error(void) { return g_err; }
+unsigned long long ganffn_launch_count(void) { return g_launches; }
+void ganffn_reset_launch_count(void) { g_launches = 0; }
+int ganffn_set_gemm_engine(int engine) {
+  int prev = g_gemm_engine;
+  if (engine >= GANFFN_GEMM_AUTO && engine <= GANFFN_GEMM_TC) g_gemm_engine = engine;
+  return prev;
+}
+
+int ganffn_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* pre,
+                      int M, int N, int K, int act, int drop_before_act, float p_drop, uint64_t seed, int site,
+                      float* scratch, int64_t scratch_floats, void* stream) {
+  GANFFN_CHECK_ARG(x && w && y, "linear_fwd: null pointer");
+  GANFFN_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "linear_fwd: dropout p=%f", p_drop);
+  Epilogue ep;
+  ep.bias = bias; ep.residual = residual; ep.ldr = N; ep.pre = pre; ep.act = act; ep.drop_before_act = drop_before_act;
+  ep.p_drop = p_drop; ep.seed = seed; ep.site = (uint32_t)site;
+  return gemm(x, K, false, w, K, true, y, N, M, N, K, ep, scratch, scratch_floats, S(stream));
+}
+
+int ganffn_linear_dgrad(const float* dy, const float* w, const float* residual, float* dx, int M, int N, int K,
+                        float* scratch, int64_t scratch_floats, void* stream) {
+  GANFFN_CHECK_ARG(dy && w && dx, "linear_dgrad: null pointer");
+  Epilogue ep;
+  ep.residual = residual; ep.ldr = K;
+  return gemm(dy, N, false, w, K, false, dx, K, M, K, N, ep, scratch, scratch_floats, S(stream));
+}
+
+int64_t ganffn_wgrad_scratch_floats(int M, int N, int K) {
+  return round_up(gemm_scratch_floats(N, K, M), 32) + colsum_scratch_floats(M, N);
+}
+
+int64_t ganffn_gemm_scratch_floats(int M, int N, int K) { return gemm_scratch_floats(M, N, K); }
+
+int ganffn_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int N, int K, int accumulate,
+                        float* scratch, void* stream) {
+  GANFFN_CHECK_ARG(dy && x && dw && scratch, "linear_wgrad: null pointer");
+  Epilogue ep;
+  ep.beta = accumulate ? 1.f : 0.f;
+  const int64_t gs = round_up(gemm_scratch_floats(N, K, M), 32);
+  GANFFN_TRY(gemm(dy, N, true, x, K, false, dw, K, N, K, M, ep, scratch, gs, S(stream)));
+  if (db) GANFFN_TRY(colsum(dy, M, N, db, accumulate, scratch + gs, S(stream)));
+  return GANFFN_OK;
+}
+
+int ganffn_attention_fwd(const float* qkv, float* o, float* lse, int S_, int B, int d, int nhead, float p_drop,
+                         uint64_t seed, int site, void* stream) {
+  GANFFN_CHECK_ARG(qkv && o && lse, "attention_fwd: null pointer");
+  return attention_fwd(qkv, o, lse, S_, B, d, nhead, p_drop, seed, site, S(stream));
+}
+
+int ganffn_attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S_,
+                         int B, int d, int nhead, float p_drop, uint64_t seed, int site, void* stream) {
+  GANFFN_CHECK_ARG(qkv && o && lse && d_o && dqkv, "attention_bwd: null pointer");
+  return attention_bwd(qkv, o, lse, d_o, dqkv, S_, B, d, nhead, p_drop, seed, site, S(stream));
+}
+
+int ganffn_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T, int d, void* stream) {
+  GANFFN_CHECK_ARG(z && gamma && beta && y, "layernorm_fwd: null pointer");
+  return layernorm_fwd(z, gamma, beta, y, T, d, S(stream));
+}
+
+int ganffn_layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
+                         float* dbeta, int T, int d, int accumulate, float p_drop, uint64_t seed, int site,
+                         float* scratch, void* stream) {
+  GANFFN_CHECK_ARG(dy && z && gamma && dz && dgamma && dbeta, "layernorm_bwd: null pointer");
+  return layernorm_bwd(dy, z, gamma, dz, dz_drop, dgamma, dbeta, T, d, accumulate, p_drop, seed, site, scratch,
+                       S(stream));
+}
+
+int64_t ganffn_layernorm_scratch_floats(int T, int d) { return layernorm_scratch_floats(T, d); }
+
+int ganffn_posenc_fwd(const float* x, const float* pe, float* y, int S_, int B, int d, float p_drop, uint64_t seed,
+                      void* stream) {
+  GANFFN_CHECK_ARG(x && pe && y, "posenc_fwd: null pointer");
+  return posenc_fwd(x, pe, y, S_, B, d, p_drop, seed, S(stream));
+}
+
+int ganffn_dropout_mask(float* out, int64_t rows, int64_t cols, int64_t row_stride, float p_drop, uint64_t seed,
+                        int site, void* stream) {
+  GANFFN_CHECK_ARG(out, "dropout_mask: null pointer");
+  return dropout_mask(out, rows, cols, row_stride, p_drop, seed, site, S(stream));
+}
+
+int ganffn_fuse_cls_fwd(const float* a, const float* v, const float* t, const float* w, const float* b, float* fusion,
+                        float* log_prob, int T, int dh, int C, void* stream) {
+  GANFFN_CHECK_ARG(a && v && t && w && b && log_prob, "fuse_cls_fwd: null pointer");
+  return fuse_cls_fwd(a, v, t, w, b, fusion, log_prob, T, dh, C, S(stream));
+}
+
+int ganffn_fuse_cls_bwd(const float* d_log_prob, const float* log_prob, const float* fusion, const float* w,
+                        float* d_fusion, float* dw, float* db, int T, int dh, int C, int accumulate, float* scratch,
+                        void* stream) {
+  GANFFN_CHECK_ARG(d_log_prob && log_prob && fusion && w && d_fusion && dw && db, "fuse_cls_bwd: null pointer");
+  return fuse_cls_bwd(d_log_prob, log_prob, fusion, w, d_fusion, dw, db, T, dh, C, accumulate, scratch, S(stream));
+}
+
+int64_t ganffn_fuse_cls_scratch_floats(int T, int dh, int C) { return fuse_cls_scratch_floats(T, dh, C); }
+
+int ganffn_masked_nll_fwd(const float* pred, const int64_t* target, const float* mask, const float* weight,
+                          float* loss_and_den, int64_t n, int C, float den_override, void* stream) {
+  GANFFN_CHECK_ARG(pred && target && mask && loss_and_den, "masked_nll_fwd: null pointer");
+  return masked_nll_fwd(pred, target, mask, weight, loss_and_den, n, C, den_override, S(stream));
+}
+
+int ganffn_masked_nll_bwd(const float* d_loss, const float* loss_and_den, const int64_t* target, const float* mask,
+                          const float* weight, float* d_pred, int64_t n, int C, void* stream) {
+  GANFFN_CHECK_ARG(d_loss && loss_and_den && target && mask && d_pred, "masked_nll_bwd: null pointer");
+  return masked_nll_bwd(d_loss, loss_and_den, target, mask, weight, d_pred, n, C, S(stream));
+}
+
+int ganffn_bce_fwd(const float* prob, const float* target, float* loss, int64_t n, float scale, void* stream) {
+  GANFFN_CHECK_ARG(prob && target && loss, "bce_fwd: null pointer");
+  return bce_fwd(prob, target, loss, n, scale, S(stream));
+}
+
+int ganffn_bce_bwd(const float* d_loss, const float* prob, const float* target, float* d_prob, int64_t n, float scale,
+                   void* stream) {
+  GANFFN_CHECK_ARG(d_loss && prob && target && d_prob, "bce_bwd: null pointer");
+  return bce_bwd(d_loss, prob, target, d_prob, n, scale, S(stream));
+}
+
+int ganffn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  GANFFN_CHECK_ARG(p && g && m && v, "adam_step: null pointer");
+  return adam_step(p, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale, S(stream));
+}
+
+static NetDims dims(int kind, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1, int h2) {
+  NetDims nd;
+  nd.kind = kind; nd.S = S_; nd.B = B; nd.d_in = d_in; nd.d = d; nd.nhead = nhead; nd.dff = dff; nd.L = nlayers;
+  nd.h1 = h1; nd.h2 = h2;
+  return nd;
+}
+
+int ganffn_net_fwd(int kind, const float* params, const int64_t* off, const float* pe, const float* x, float* out,
+                   float* stash, float* scratch, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1,
+                   int h2, int train, float p_head, uint64_t seed, void* stream) {
+  return net_fwd(dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2), params, off, pe, x, out, stash, scratch, train,
+                 p_head, seed, S(stream));
+}
+
+int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const float* x, const float* out,
+                   const float* d_out_grad, const float* stash, float* grads, float* dx, float* scratch, int S_, int B,
+                   int d_in, int d, int nhead, int dff, int nlayers, int h1, int h2, int train, float p_head,
+                   uint64_t seed, int accumulate, void* stream) {
+  return net_bwd(dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2), params, off, x, out, d_out_grad, stash, grads,
+                 dx, scratch, train, p_head, seed, accumulate, S(stream));
+}
+
+int64_t ganffn_net_stash_floats(int kind, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1,
+                                int h2) {
+  NetDims nd = dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2);
+  if (net_check(nd) != GANFFN_OK) return -1;
+  return net_stash_floats(nd);
+}
+
+int64_t ganffn_net_scratch_floats(int kind, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1,
+                                  int h2) {
+  NetDims nd = dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2);
+  if (net_check(nd) != GANFFN_OK) return -1;
+  return net_scratch_floats(nd);
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// Shared device/host helpers for the GAN-FFN sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include <algorithm>
+
+#include "../../include/ganffn.h"
+
+namespace ganffn {
+
+// ---- library state (defined in capi.cu) ------------------------------------------------
+extern unsigned long long g_launches;
+extern int g_gemm_engine;
+void set_error(const char* fmt, ...);
+
+#define GANFFN_CHECK_ARG(cond, ...)                \
+  do {                                             \
+    if (!(cond)) {                                 \
+      ::ganffn::set_error(__VA_ARGS__);            \
+      return GANFFN_ERR_ARG;                       \
+    }                                              \
+  } while (0)
+
+// Call after every kernel launch: counts it and turns a launch error into a status code.
+#define GANFFN_LAUNCHED(name)                                                     \
+  do {                                                                            \
+    ++::ganffn::g_launches;                                                       \
+    cudaError_t e__ = cudaPeekAtLastError();                                      \
+    if (e__ != cudaSuccess) {                                                     \
+      ::ganffn::set_error("%s: %s", name, cudaGetErrorString(e__));               \
+      return GANFFN_ERR_CUDA;                                                     \
+    }                                                                             \
+  } while (0)
+
+#define GANFFN_TRY(expr)             \
+  do {                               \
+    int rc__ = (expr);               \
+    if (rc__ != GANFFN_OK) return rc__; \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- Philox4x32-10 -----------------------------------------------------------------------
+// counter = (group_lo, group_hi, site, 0), key = (seed_lo, seed_hi).  One call yields the four
+// uniforms of elements 4*group .. 4*group+3 of a dropout site.
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint32_t site, uint64_t group) {
+  uint32_t c0 = (uint32_t)group, c1 = (uint32_t)(group >> 32), c2 = site, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Scaled keep mask of element `e` (0 or 1/(1-p)).  keep <=> uniform >= p.
+__device__ __forceinline__ float keep_from_bits(uint32_t bits, float p, float scale) {
+  float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? scale : 0.0f;
+}
+
+__device__ __forceinline__ float dropout_scale1(uint64_t seed, uint32_t site, uint64_t e, float p, float scale) {
+  uint4 r = philox4x32_10(seed, site, e >> 2);
+  uint32_t lane = (uint32_t)(e & 3);
+  uint32_t bits = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+  return keep_from_bits(bits, p, scale);
+}
+
+// Four consecutive elements e..e+3.  Fast path when e is 4-aligned.
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t site, uint64_t e, float p, float scale,
+                                               float out[4]) {
+  if ((e & 3) == 0) {
+    uint4 r = philox4x32_10(seed, site, e >> 2);
+    out[0] = keep_from_bits(r.x, p, scale);
+    out[1] = keep_from_bits(r.y, p, scale);
+    out[2] = keep_from_bits(r.z, p, scale);
+    out[3] = keep_from_bits(r.w, p, scale);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = dropout_scale1(seed, site, e + j, p, scale);
+  }
+}
+
+// ---- activations ---------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float inv_sqrt_2pi = 0.39894228040143267794f;
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * inv_sqrt_2pi * expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case GANFFN_ACT_RELU: return v > 0.0f ? v : 0.0f;
+    case GANFFN_ACT_GELU: return gelu_f(v);
+    case GANFFN_ACT_SIGMOID: return sigmoid_f(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- GEMM epilogue shared by the SIMT and tcgen05 engines --------------------------------------
+// Backward-activation codes (dact)
+enum { DACT_NONE = 0, DACT_NONZERO = 1, DACT_GELU = 2 };
+
+struct Epilogue {
+  const float* bias = nullptr;      // [N]
+  const float* residual = nullptr;  // [M, ldr], added last
+  int ldr = 0;
+  float* pre = nullptr;             // [M, ldc] optional: value fed to act
+  int act = GANFFN_ACT_NONE;
+  int drop_before_act = 0;
+  float p_drop = 0.0f;              // forward dropout (or backward mask regeneration for dact)
+  uint64_t seed = 0;
+  uint32_t site = 0;
+  // backward-through-activation: v *= f(dact_src[m,n])
+  int dact = DACT_NONE;
+  const float* dact_src = nullptr;  // [M, ldc]
+  float dact_scale = 1.0f;          // DACT_NONZERO: multiply kept lanes by this (1/(1-p))
+  float beta = 0.0f;                // C = beta*C + v
+};
+
+// Applies the epilogue to the four accumulators of row m, columns n..n+3 (n % 4 == 0) and
+// stores the valid ones.  N is the logical row length (also the dropout index stride).
+__device__ __forceinline__ void epilogue_store4(const Epilogue& ep, float* C, int ldc, int M, int N, int m, int n,
+                                                float v[4]) {
+  if (m >= M || n >= N) return;
+  const int nv = min(4, N - n);
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) v[j] += __ldg(ep.bias + n + j);
+  }
+  const bool drop = ep.p_drop > 0.0f;
+  float msk[4] = {1.f, 1.f, 1.f, 1.f};
+  if (drop) dropout_scale4(ep.seed, ep.site, (uint64_t)m * (uint64_t)N + (uint64_t)n, ep.p_drop, 1.0f / (1.0f - ep.p_drop), msk);
+  if (ep.dact == DACT_NONE) {
+    if (drop && ep.drop_before_act) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= msk[j];
+    }
+    if (ep.pre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nv) ep.pre[(size_t)m * ldc + n + j] = v[j];
+    }
+    if (ep.act != GANFFN_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], ep.act);
+    }
+    if (drop && !ep.drop_before_act) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= msk[j];
+    }
+  } else if (ep.dact == DACT_NONZERO) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) v[j] = (ep.dact_src[(size_t)m * ldc + n + j] != 0.0f) ? v[j] * ep.dact_scale : 0.0f;
+  } else {  // DACT_GELU: v *= gelu'(pre) * dropmask
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) v[j] *= gelu_grad_f(ep.dact_src[(size_t)m * ldc + n + j]) * msk[j];
+  }
+  if (ep.residual) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) v[j] += ep.residual[(size_t)m * ep.ldr + n + j];
+  }
+  float* c = C + (size_t)m * ldc + n;
+  if (ep.beta != 0.0f) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) v[j] += ep.beta * c[j];
+  }
+  if (nv == 4 && ((((uintptr_t)c) & 15) == 0)) {
+    *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) c[j] = v[j];
+  }
+}
+
+// ---- GEMM front door (gemm.cu): C[M,N] = op(A)[M,K] * op(B)[K,N] with epilogue -----------------
+//   transA = false: A stored [M, lda] (k contiguous);  true: A stored [K, lda] (m contiguous)
+//   b_is_nk = true: B stored [N, ldb] (k contiguous, i.e. nn.Linear weight); false: stored [K, ldb]
+// scratch is used for split-K partials (may be null => no split).
+int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
+         int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st);
+int64_t gemm_scratch_floats(int M, int N, int K);
+
+}  // namespace ganffn

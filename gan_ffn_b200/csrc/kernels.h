@@ -1,0 +1,71 @@
+// Internal (C++) entry points of the kernel files; capi.cu wraps them as the C ABI.
+#pragma once
+#include "common.cuh"
+
+namespace ganffn {
+
+// gemm_simt.cu
+int gemm_simt(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M,
+              int N, int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st);
+int64_t gemm_simt_scratch_floats(int M, int N, int K);
+
+// gemm_tc.cu (tcgen05 3xTF32)
+bool gemm_tc_supported(bool transA, bool b_is_nk, int lda, int ldb, int ldc, int M, int N, int K, const void* A,
+                       const void* B);
+int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
+            int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st);
+int64_t gemm_tc_scratch_floats(int M, int N, int K);
+
+// attention.cu
+int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, uint64_t seed,
+                  int site, cudaStream_t st);
+int attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
+                  int nhead, float p, uint64_t seed, int site, cudaStream_t st);
+
+// rowwise.cu
+int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T, int d, cudaStream_t st);
+int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
+                  float* dbeta, int T, int d, int accumulate, float p, uint64_t seed, int site, float* scratch,
+                  cudaStream_t st);
+int64_t layernorm_scratch_floats(int T, int d);
+int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, uint64_t seed, cudaStream_t st);
+enum { EW_GELU_DROP = 0, EW_DGELU_MASK = 1, EW_DSIGMOID_MASK = 2, EW_MASK = 3 };
+int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, uint64_t seed, int site,
+                cudaStream_t st);
+int colsum(const float* a, int M, int N, float* out, int accumulate, float* scratch, cudaStream_t st);
+int64_t colsum_scratch_floats(int M, int N);
+int dropout_mask(float* out, int64_t rows, int64_t cols, int64_t row_stride, float p, uint64_t seed, int site,
+                 cudaStream_t st);
+
+// losses.cu
+int fuse_cls_fwd(const float* a, const float* v, const float* t, const float* w, const float* b, float* fusion,
+                 float* logp, int T, int dh, int C, cudaStream_t st);
+int fuse_cls_bwd(const float* dlp, const float* logp, const float* fusion, const float* w, float* d_fusion, float* dw,
+                 float* db, int T, int dh, int C, int accumulate, float* scratch, cudaStream_t st);
+int64_t fuse_cls_scratch_floats(int T, int dh, int C);
+int masked_nll_fwd(const float* pred, const int64_t* target, const float* mask, const float* weight, float* out,
+                   int64_t n, int C, float den_override, cudaStream_t st);
+int masked_nll_bwd(const float* d_loss, const float* loss_and_den, const int64_t* target, const float* mask,
+                   const float* weight, float* d_pred, int64_t n, int C, cudaStream_t st);
+int bce_fwd(const float* prob, const float* target, float* loss, int64_t n, float scale, cudaStream_t st);
+int bce_bwd(const float* d_loss, const float* prob, const float* target, float* d_prob, int64_t n, float scale,
+            cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2, float eps,
+              float wd, float gscale, cudaStream_t st);
+
+// net.cu
+struct NetDims {
+  int kind, S, B, d_in, d, nhead, dff, L, h1, h2;
+  int T() const { return S * B; }
+  bool has_object() const { return d_in != d; }
+};
+int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const float* pe, const float* x, float* out,
+            float* stash, float* scratch, int train, float p_head, uint64_t seed, cudaStream_t st);
+int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const float* x, const float* out,
+            const float* d_out, const float* stash, float* grads, float* dx, float* scratch, int train, float p_head,
+            uint64_t seed, int accumulate, cudaStream_t st);
+int64_t net_stash_floats(const NetDims& nd);
+int64_t net_scratch_floats(const NetDims& nd);
+int net_check(const NetDims& nd);
+
+}  // namespace ganffn

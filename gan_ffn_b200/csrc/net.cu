@@ -1,0 +1,303 @@
+// Whole-network forward / backward: [object] -> PE -> L encoder layers -> head, as one host-side
+// sequence of kernel launches on the caller's stream (no allocation, no synchronisation, so the
+// whole sequence can be captured into a CUDA graph by the caller).
+//
+// Reference: generators model.py:1221-1231, 1255-1263, 1286-1294; discriminators model.py:1320-1327,
+// 1354-1364, 1390-1397; encoder layer torch/nn/modules/transformer.py:944-982 (post-norm, ReLU).
+#include "kernels.h"
+
+namespace ganffn {
+
+namespace {
+
+constexpr float P_PE = 0.2f;   // model.py:1179
+constexpr float P_ENC = 0.1f;  // torch TransformerEncoderLayer default
+
+inline int64_t al(int64_t n) { return round_up(n, 32); }  // 128-byte aligned regions
+
+// parameter table indices (see include/ganffn.h)
+enum { IN_W = 0, IN_B, OUT_W, OUT_B, L1_W, L1_B, L2_W, L2_B, N1_W, N1_B, N2_W, N2_B, PER_LAYER };
+enum { FC1_W = 0, FC1_B, FC2_W, FC2_B, FC3_W, FC3_B, OBJ_W, OBJ_B };
+
+struct Stash {
+  int64_t obj, x0, layer0, per_layer, qkv, lse, o, z1, x1, h, z2, x2, g0, f1, a1, f2, a2, total;
+};
+
+Stash stash_layout(const NetDims& nd) {
+  Stash s;
+  const int64_t T = nd.T(), d = nd.d;
+  int64_t p = 0;
+  s.obj = p; if (nd.has_object()) p += al(T * d);
+  s.x0 = p; p += al(T * d);
+  s.layer0 = p;
+  int64_t q = 0;
+  s.qkv = q; q += al(T * 3 * d);
+  s.lse = q; q += al((int64_t)nd.B * nd.nhead * nd.S);
+  s.o = q; q += al(T * d);
+  s.z1 = q; q += al(T * d);
+  s.x1 = q; q += al(T * d);
+  s.h = q; q += al(T * nd.dff);
+  s.z2 = q; q += al(T * d);
+  s.x2 = q; q += al(T * d);
+  s.per_layer = q;
+  p += q * nd.L;
+  s.g0 = p; p += al(T * d);
+  s.f1 = p; p += al(T * nd.h1);
+  s.a1 = p; p += al(T * nd.h1);
+  s.f2 = p; p += al(T * nd.h2);
+  s.a2 = p; if (nd.kind == GANFFN_NET_DISCRIMINATOR) p += al(T * nd.h2);
+  s.total = p;
+  return s;
+}
+
+struct Scratch {
+  int64_t da, db, dz, dzd, d_o, dqkv, dh, hb1, hb2, hb3, gemm, gemm_floats, red, total;
+};
+
+Scratch scratch_layout(const NetDims& nd) {
+  Scratch s;
+  const int64_t T = nd.T(), d = nd.d;
+  int64_t p = 0;
+  s.da = p; p += al(T * d);
+  s.db = p; p += al(T * d);
+  s.dz = p; p += al(T * d);
+  s.dzd = p; p += al(T * d);
+  s.d_o = p; p += al(T * d);
+  s.dqkv = p; p += al(T * 3 * d);
+  s.dh = p; p += al(T * nd.dff);
+  s.hb1 = p; p += al(T * nd.h1);
+  s.hb2 = p; p += al(T * nd.h2);
+  s.hb3 = p; p += al(T);
+  int64_t g = 0;
+  auto mx = [&](int M, int N, int K) {
+    g = std::max(g, gemm_scratch_floats(M, N, K));
+  };
+  const int Ti = (int)T;
+  // forward + dgrad shapes
+  mx(Ti, 3 * nd.d, nd.d); mx(Ti, nd.d, nd.d); mx(Ti, nd.dff, nd.d); mx(Ti, nd.d, nd.dff); mx(Ti, nd.d, 3 * nd.d);
+  mx(Ti, nd.h1, nd.d); mx(Ti, nd.h2, nd.h1); mx(Ti, nd.h1, nd.h2); mx(Ti, nd.d, nd.h1); mx(Ti, 1, nd.h2); mx(Ti, nd.h2, 1);
+  if (nd.has_object()) { mx(Ti, nd.d, nd.d_in); mx(Ti, nd.d_in, nd.d); mx(nd.d, nd.d_in, Ti); }
+  // wgrad shapes
+  mx(3 * nd.d, nd.d, Ti); mx(nd.d, nd.d, Ti); mx(nd.dff, nd.d, Ti); mx(nd.d, nd.dff, Ti);
+  mx(nd.h1, nd.d, Ti); mx(nd.h2, nd.h1, Ti); mx(1, nd.h2, Ti);
+  s.gemm = p; s.gemm_floats = al(g); p += s.gemm_floats;
+  int64_t r = layernorm_scratch_floats(Ti, nd.d);
+  r = std::max(r, colsum_scratch_floats(Ti, nd.dff));
+  r = std::max(r, colsum_scratch_floats(Ti, 3 * nd.d));
+  r = std::max(r, colsum_scratch_floats(Ti, std::max(nd.h1, nd.d)));
+  s.red = p; p += al(r);
+  s.total = p;
+  return s;
+}
+
+struct Ctx {
+  const NetDims& nd;
+  float* gemm_scratch;
+  int64_t gemm_floats;
+  float* red;
+  cudaStream_t st;
+
+  int linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int N, int K, Epilogue ep) const {
+    ep.bias = b;
+    return gemm(x, K, false, w, K, true, y, N, M, N, K, ep, gemm_scratch, gemm_floats, st);
+  }
+  int dgrad(const float* dy, const float* w, float* dx, int M, int N, int K, Epilogue ep) const {
+    return gemm(dy, N, false, w, K, false, dx, K, M, K, N, ep, gemm_scratch, gemm_floats, st);
+  }
+  int wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K, int accumulate) const {
+    Epilogue ep;
+    ep.beta = accumulate ? 1.f : 0.f;
+    GANFFN_TRY(gemm(dy, N, true, x, K, false, dw, K, N, K, M, ep, gemm_scratch, gemm_floats, st));
+    if (dbias) GANFFN_TRY(colsum(dy, M, N, dbias, accumulate, red, st));
+    return GANFFN_OK;
+  }
+};
+
+}  // namespace
+
+int net_check(const NetDims& nd) {
+  GANFFN_CHECK_ARG(nd.kind == GANFFN_NET_GENERATOR || nd.kind == GANFFN_NET_DISCRIMINATOR, "net: kind %d", nd.kind);
+  GANFFN_CHECK_ARG(nd.S >= 1 && nd.S <= GANFFN_MAX_SEQ, "net: seq_len %d outside [1,%d] (PositionalEncoding max_len, model.py:1179)",
+                   nd.S, GANFFN_MAX_SEQ);
+  GANFFN_CHECK_ARG(nd.B >= 1, "net: batch %d", nd.B);
+  GANFFN_CHECK_ARG(nd.d > 0 && nd.d % 4 == 0 && nd.d <= 512, "net: d_model %d must be a multiple of 4 and <= 512", nd.d);
+  GANFFN_CHECK_ARG(nd.nhead > 0 && nd.d % nd.nhead == 0, "net: d_model %d not divisible by nhead %d", nd.d, nd.nhead);
+  GANFFN_CHECK_ARG(nd.dff > 0 && nd.dff % 4 == 0 && nd.L >= 1, "net: dff %d / layers %d", nd.dff, nd.L);
+  GANFFN_CHECK_ARG(nd.h1 > 0 && nd.h2 > 0 && nd.h1 % 4 == 0 && nd.h2 % 4 == 0, "net: head widths %d,%d must be multiples of 4", nd.h1, nd.h2);
+  GANFFN_CHECK_ARG(nd.d_in == nd.d || (nd.kind == GANFFN_NET_DISCRIMINATOR && nd.d_in % 4 == 0),
+                   "net: input width %d does not match d_model %d (only the visual discriminator projects, model.py:1355)",
+                   nd.d_in, nd.d);
+  return GANFFN_OK;
+}
+
+int64_t net_stash_floats(const NetDims& nd) { return stash_layout(nd).total; }
+int64_t net_scratch_floats(const NetDims& nd) { return scratch_layout(nd).total; }
+
+int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const float* pe, const float* x, float* out,
+            float* stash, float* scratch, int train, float p_head, uint64_t seed, cudaStream_t st) {
+  GANFFN_TRY(net_check(nd));
+  GANFFN_CHECK_ARG(params && off && pe && x && out && stash && scratch, "net_fwd: null pointer");
+  const Stash sl = stash_layout(nd);
+  const Scratch sc = scratch_layout(nd);
+  const Ctx cx{nd, scratch + sc.gemm, sc.gemm_floats, scratch + sc.red, st};
+  const int T = nd.T(), d = nd.d;
+  const float p_pe = train ? P_PE : 0.f, p_enc = train ? P_ENC : 0.f, p_hd = train ? p_head : 0.f;
+  const int64_t* hoff = off + (int64_t)nd.L * PER_LAYER;
+  auto P = [&](int64_t o) { return params + o; };
+
+  const float* xin = x;
+  if (nd.has_object()) {
+    GANFFN_CHECK_ARG(hoff[OBJ_W] >= 0, "net_fwd: input is %d wide but the network has no `object` projection", nd.d_in);
+    GANFFN_TRY(cx.linear_fwd(x, P(hoff[OBJ_W]), P(hoff[OBJ_B]), stash + sl.obj, T, d, nd.d_in, Epilogue{}));
+    xin = stash + sl.obj;
+  }
+  GANFFN_TRY(posenc_fwd(xin, pe, stash + sl.x0, nd.S, nd.B, d, p_pe, seed, st));
+
+  const float* cur = stash + sl.x0;
+  for (int l = 0; l < nd.L; ++l) {
+    float* base = stash + sl.layer0 + (int64_t)l * sl.per_layer;
+    const int64_t* lo = off + (int64_t)l * PER_LAYER;
+    GANFFN_TRY(cx.linear_fwd(cur, P(lo[IN_W]), P(lo[IN_B]), base + sl.qkv, T, 3 * d, d, Epilogue{}));
+    GANFFN_TRY(attention_fwd(base + sl.qkv, base + sl.o, base + sl.lse, nd.S, nd.B, d, nd.nhead, p_enc, seed,
+                             GANFFN_SITE_LAYER(l, 0), st));
+    {
+      Epilogue ep; ep.p_drop = p_enc; ep.seed = seed; ep.site = GANFFN_SITE_LAYER(l, 1);
+      ep.residual = cur; ep.ldr = d;
+      GANFFN_TRY(cx.linear_fwd(base + sl.o, P(lo[OUT_W]), P(lo[OUT_B]), base + sl.z1, T, d, d, ep));
+    }
+    GANFFN_TRY(layernorm_fwd(base + sl.z1, P(lo[N1_W]), P(lo[N1_B]), base + sl.x1, T, d, st));
+    {
+      Epilogue ep; ep.act = GANFFN_ACT_RELU; ep.p_drop = p_enc; ep.seed = seed; ep.site = GANFFN_SITE_LAYER(l, 2);
+      GANFFN_TRY(cx.linear_fwd(base + sl.x1, P(lo[L1_W]), P(lo[L1_B]), base + sl.h, T, nd.dff, d, ep));
+    }
+    {
+      Epilogue ep; ep.p_drop = p_enc; ep.seed = seed; ep.site = GANFFN_SITE_LAYER(l, 3);
+      ep.residual = base + sl.x1; ep.ldr = d;
+      GANFFN_TRY(cx.linear_fwd(base + sl.h, P(lo[L2_W]), P(lo[L2_B]), base + sl.z2, T, d, nd.dff, ep));
+    }
+    GANFFN_TRY(layernorm_fwd(base + sl.z2, P(lo[N2_W]), P(lo[N2_B]), base + sl.x2, T, d, st));
+    cur = base + sl.x2;
+  }
+
+  // head
+  const bool gen = nd.kind == GANFFN_NET_GENERATOR;
+  GANFFN_TRY(elementwise(cur, nullptr, stash + sl.g0, (int64_t)T * d, EW_GELU_DROP, gen ? p_hd : 0.f, seed,
+                         GANFFN_SITE_HEAD + 0, st));
+  {
+    Epilogue ep; ep.act = GANFFN_ACT_GELU; ep.drop_before_act = 1; ep.p_drop = p_hd; ep.seed = seed;
+    ep.site = GANFFN_SITE_HEAD + 1; ep.pre = stash + sl.f1;
+    GANFFN_TRY(cx.linear_fwd(stash + sl.g0, P(hoff[FC1_W]), P(hoff[FC1_B]), stash + sl.a1, T, nd.h1, d, ep));
+  }
+  {
+    Epilogue ep; ep.act = GANFFN_ACT_GELU; ep.drop_before_act = 1; ep.p_drop = p_hd; ep.seed = seed;
+    ep.site = GANFFN_SITE_HEAD + 2; ep.pre = stash + sl.f2;
+    float* dst = gen ? out : stash + sl.a2;
+    GANFFN_TRY(cx.linear_fwd(stash + sl.a1, P(hoff[FC2_W]), P(hoff[FC2_B]), dst, T, nd.h2, nd.h1, ep));
+  }
+  if (!gen) {
+    Epilogue ep; ep.act = GANFFN_ACT_SIGMOID; ep.drop_before_act = 1; ep.p_drop = p_hd; ep.seed = seed;
+    ep.site = GANFFN_SITE_HEAD + 3;
+    GANFFN_TRY(cx.linear_fwd(stash + sl.a2, P(hoff[FC3_W]), P(hoff[FC3_B]), out, T, 1, nd.h2, ep));
+  }
+  return GANFFN_OK;
+}
+
+int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const float* x, const float* out,
+            const float* d_out, const float* stash, float* grads, float* dx, float* scratch, int train, float p_head,
+            uint64_t seed, int accumulate, cudaStream_t st) {
+  GANFFN_TRY(net_check(nd));
+  GANFFN_CHECK_ARG(params && off && x && out && d_out && stash && grads && scratch, "net_bwd: null pointer");
+  const Stash sl = stash_layout(nd);
+  const Scratch sc = scratch_layout(nd);
+  const Ctx cx{nd, scratch + sc.gemm, sc.gemm_floats, scratch + sc.red, st};
+  const int T = nd.T(), d = nd.d;
+  const float p_pe = train ? P_PE : 0.f, p_enc = train ? P_ENC : 0.f, p_hd = train ? p_head : 0.f;
+  const int64_t* hoff = off + (int64_t)nd.L * PER_LAYER;
+  auto P = [&](int64_t o) { return params + o; };
+  auto G = [&](int64_t o) { return grads + o; };
+  const bool gen = nd.kind == GANFFN_NET_GENERATOR;
+
+  float* da = scratch + sc.da;    // gradient w.r.t. the current layer output
+  float* db = scratch + sc.db;
+  float* dz = scratch + sc.dz;
+  float* dzd_buf = scratch + sc.dzd;
+  float* hb1 = scratch + sc.hb1;
+  float* hb2 = scratch + sc.hb2;
+  float* hb3 = scratch + sc.hb3;
+  const float* last_x2 = stash + sl.layer0 + (int64_t)(nd.L - 1) * sl.per_layer + sl.x2;
+
+  // ---- head ----
+  if (gen) {
+    // out = gelu(f2), f2 = drop(fc2(a1))
+    GANFFN_TRY(elementwise(d_out, stash + sl.f2, hb2, (int64_t)T * nd.h2, EW_DGELU_MASK, p_hd, seed, GANFFN_SITE_HEAD + 2, st));
+  } else {
+    // prob = sigmoid(drop(fc3(a2)))
+    GANFFN_TRY(elementwise(d_out, out, hb3, (int64_t)T, EW_DSIGMOID_MASK, p_hd, seed, GANFFN_SITE_HEAD + 3, st));
+    GANFFN_TRY(cx.wgrad(hb3, stash + sl.a2, G(hoff[FC3_W]), G(hoff[FC3_B]), T, 1, nd.h2, accumulate));
+    Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = stash + sl.f2; ep.p_drop = p_hd; ep.seed = seed;
+    ep.site = GANFFN_SITE_HEAD + 2;
+    GANFFN_TRY(cx.dgrad(hb3, P(hoff[FC3_W]), hb2, T, 1, nd.h2, ep));
+  }
+  GANFFN_TRY(cx.wgrad(hb2, stash + sl.a1, G(hoff[FC2_W]), G(hoff[FC2_B]), T, nd.h2, nd.h1, accumulate));
+  {
+    Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = stash + sl.f1; ep.p_drop = p_hd; ep.seed = seed;
+    ep.site = GANFFN_SITE_HEAD + 1;
+    GANFFN_TRY(cx.dgrad(hb2, P(hoff[FC2_W]), hb1, T, nd.h2, nd.h1, ep));
+  }
+  GANFFN_TRY(cx.wgrad(hb1, stash + sl.g0, G(hoff[FC1_W]), G(hoff[FC1_B]), T, nd.h1, d, accumulate));
+  {
+    Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = last_x2; ep.p_drop = gen ? p_hd : 0.f; ep.seed = seed;
+    ep.site = GANFFN_SITE_HEAD + 0;
+    GANFFN_TRY(cx.dgrad(hb1, P(hoff[FC1_W]), da, T, nd.h1, d, ep));
+  }
+
+  // ---- encoder layers, last to first ----
+  for (int l = nd.L - 1; l >= 0; --l) {
+    const float* base = stash + sl.layer0 + (int64_t)l * sl.per_layer;
+    const int64_t* lo = off + (int64_t)l * PER_LAYER;
+    const float* xin = l == 0 ? stash + sl.x0 : stash + sl.layer0 + (int64_t)(l - 1) * sl.per_layer + sl.x2;
+    float* dzd = p_enc > 0.f ? dzd_buf : dz;
+
+    // x2 = LN2(z2), z2 = x1 + drop(linear2(h))
+    GANFFN_TRY(layernorm_bwd(da, base + sl.z2, P(lo[N2_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N2_W]), G(lo[N2_B]),
+                             T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 3), cx.red, st));
+    GANFFN_TRY(cx.wgrad(dzd, base + sl.h, G(lo[L2_W]), G(lo[L2_B]), T, d, nd.dff, accumulate));
+    {
+      Epilogue ep; ep.dact = DACT_NONZERO; ep.dact_src = base + sl.h; ep.dact_scale = p_enc > 0.f ? 1.f / (1.f - p_enc) : 1.f;
+      GANFFN_TRY(cx.dgrad(dzd, P(lo[L2_W]), scratch + sc.dh, T, d, nd.dff, ep));
+    }
+    GANFFN_TRY(cx.wgrad(scratch + sc.dh, base + sl.x1, G(lo[L1_W]), G(lo[L1_B]), T, nd.dff, d, accumulate));
+    {
+      Epilogue ep; ep.residual = dz; ep.ldr = d;
+      GANFFN_TRY(cx.dgrad(scratch + sc.dh, P(lo[L1_W]), db, T, nd.dff, d, ep));
+    }
+    // x1 = LN1(z1), z1 = xin + drop(out_proj(o))
+    GANFFN_TRY(layernorm_bwd(db, base + sl.z1, P(lo[N1_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N1_W]), G(lo[N1_B]),
+                             T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 1), cx.red, st));
+    GANFFN_TRY(cx.wgrad(dzd, base + sl.o, G(lo[OUT_W]), G(lo[OUT_B]), T, d, d, accumulate));
+    GANFFN_TRY(cx.dgrad(dzd, P(lo[OUT_W]), scratch + sc.d_o, T, d, d, Epilogue{}));
+    GANFFN_TRY(attention_bwd(base + sl.qkv, base + sl.o, base + sl.lse, scratch + sc.d_o, scratch + sc.dqkv, nd.S, nd.B,
+                             d, nd.nhead, p_enc, seed, GANFFN_SITE_LAYER(l, 0), st));
+    GANFFN_TRY(cx.wgrad(scratch + sc.dqkv, xin, G(lo[IN_W]), G(lo[IN_B]), T, 3 * d, d, accumulate));
+    {
+      Epilogue ep; ep.residual = dz; ep.ldr = d;
+      GANFFN_TRY(cx.dgrad(scratch + sc.dqkv, P(lo[IN_W]), da, T, 3 * d, d, ep));
+    }
+  }
+
+  // ---- positional encoding (dropout only) and the optional `object` projection ----
+  if (nd.has_object()) {
+    const float* dpe = da;
+    if (p_pe > 0.f) {
+      GANFFN_TRY(elementwise(da, nullptr, db, (int64_t)T * d, EW_MASK, p_pe, seed, GANFFN_SITE_PE, st));
+      dpe = db;
+    }
+    GANFFN_TRY(cx.wgrad(dpe, x, G(hoff[OBJ_W]), G(hoff[OBJ_B]), T, d, nd.d_in, accumulate));
+    if (dx) GANFFN_TRY(cx.dgrad(dpe, P(hoff[OBJ_W]), dx, T, d, nd.d_in, Epilogue{}));
+  } else if (dx) {
+    GANFFN_TRY(elementwise(da, nullptr, dx, (int64_t)T * d, EW_MASK, p_pe, seed, GANFFN_SITE_PE, st));
+  }
+  return GANFFN_OK;
+}
+
+}  // namespace ganffn

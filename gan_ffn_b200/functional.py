@@ -1,0 +1,307 @@
+"""Autograd bridges between PyTorch tensors and the C ABI (``include/ganffn.h``).
+
+PyTorch is plumbing here: it owns device memory, the stream and the autograd graph
+between networks.  Every number is produced by ``libganffn.so``.  Each ``Function``
+hands raw device pointers to one C entry point in ``forward`` and one in ``backward``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import lib, ptr
+
+# --------------------------------------------------------------------------------------
+# dropout seed stream
+# --------------------------------------------------------------------------------------
+_MASK64 = (1 << 64) - 1
+_seed_state = {"base": None, "ctr": 0}
+
+
+def manual_seed(seed: int) -> None:
+    """Re-seeds the dropout stream of the kernels (independent of torch's generators)."""
+    _seed_state["base"] = int(seed) & _MASK64
+    _seed_state["ctr"] = 0
+
+
+def next_seed() -> int:
+    if _seed_state["base"] is None:
+        _seed_state["base"] = int(torch.initial_seed()) & _MASK64
+    _seed_state["ctr"] += 1
+    x = (_seed_state["base"] * 0x9E3779B97F4A7C15 + _seed_state["ctr"] * 0xD1B54A32D192ED03) & _MASK64
+    x ^= x >> 31
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: got a {t.device} tensor. gan_ffn_b200 computes only with its sm_100a CUDA kernels; "
+            "there is no CPU fallback (use oracle/ for CPU checking).")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what}: expected float32, got {t.dtype}")
+
+
+_scratch: Dict[Tuple[str, int], torch.Tensor] = {}
+
+
+def scratch(device: torch.device, floats: int, tag: str = "main") -> torch.Tensor:
+    """A grow-only workspace per (device, tag).  All kernels of this package are issued on
+    the current stream, so one workspace per device is safe to share between calls."""
+    key = (tag, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < floats:
+        buf = torch.empty(max(int(floats), 1), dtype=torch.float32, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def _al(n: int, a: int = 32) -> int:
+    return (n + a - 1) // a * a
+
+
+# --------------------------------------------------------------------------------------
+# flat parameter arena
+# --------------------------------------------------------------------------------------
+class ParamArena:
+    """One contiguous fp32 buffer for all *live* parameters of a network and a twin buffer
+    for their gradients.  The ``nn.Parameter`` objects keep their names (so ``state_dict``
+    keys match the reference) but their ``.data`` become views into ``flat`` and their
+    ``.grad`` views into ``grad``.  One pointer + an offset table is all the C side needs;
+    Adam and the NCCL gradient all-reduce each become a single call over the arena."""
+
+    def __init__(self, params: List[torch.nn.Parameter], table: List[Optional[torch.nn.Parameter]]):
+        dev = params[0].device
+        offs, total = {}, 0
+        for p in params:
+            offs[id(p)] = total
+            total += _al(p.numel())
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params = params
+        self.grad_views = []
+        with torch.no_grad():
+            for p in params:
+                o = offs[id(p)]
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
+        self.table = np.array([-1 if p is None else offs[id(p)] for p in table], dtype=np.int64)
+        self.numel = total
+        self.sentinel = params[0]
+        self.requires_grad = any(p.requires_grad for p in params)
+
+    def valid_for(self, dev: torch.device) -> bool:
+        o = 0
+        return (self.flat.device == dev and self.sentinel.data_ptr() == self.flat.data_ptr() + 4 * o
+                and self.params[-1].device == dev)
+
+    def grads_live(self) -> bool:
+        g = self.sentinel.grad
+        return g is not None and g.data_ptr() == self.grad_views[0].data_ptr()
+
+    def install_grads(self) -> None:
+        for p, gv in zip(self.params, self.grad_views):
+            if p.requires_grad:
+                p.grad = gv
+
+
+# --------------------------------------------------------------------------------------
+# whole-network function
+# --------------------------------------------------------------------------------------
+class NetSpec:
+    """Static description of one generator / discriminator (mirrors the C NetDims)."""
+
+    def __init__(self, kind: int, d: int, nhead: int, dff: int, nlayers: int, h1: int, h2: int):
+        self.kind, self.d, self.nhead, self.dff, self.nlayers, self.h1, self.h2 = kind, d, nhead, dff, nlayers, h1, h2
+
+    def dims(self, S: int, B: int, d_in: int):
+        return (self.kind, S, B, d_in, self.d, self.nhead, self.dff, self.nlayers, self.h1, self.h2)
+
+
+class _NetFunction(torch.autograd.Function):
+    """forward: ganffn_net_fwd; backward: ganffn_net_bwd.  Parameter gradients are written
+    straight into the arena's gradient buffer (accumulating when the buffer is live), so the
+    only autograd edge is the input ``x``."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, arena: ParamArena, spec: NetSpec, pe, train: bool, p_head: float, seed: int):
+        L = lib()
+        S, B, d_in = x.shape
+        dims = spec.dims(S, B, d_in)
+        stash_n = L.query("ganffn_net_stash_floats", *dims)
+        scratch_n = L.query("ganffn_net_scratch_floats", *dims)
+        stash = torch.empty(stash_n, dtype=torch.float32, device=x.device)
+        ws = scratch(x.device, scratch_n)
+        out = torch.empty((S, B, spec.h2 if spec.kind == 0 else 1), dtype=torch.float32, device=x.device)
+        L.call("ganffn_net_fwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(pe), ptr(x), ptr(out),
+               ptr(stash), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff, spec.nlayers, spec.h1, spec.h2,
+               int(train), float(p_head), seed, _stream(x))
+        ctx.arena, ctx.spec, ctx.train, ctx.p_head, ctx.seed = arena, spec, train, p_head, seed
+        ctx.stash = stash
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = lib()
+        (x, out), arena, spec = ctx.saved_tensors, ctx.arena, ctx.spec
+        S, B, d_in = x.shape
+        dims = spec.dims(S, B, d_in)
+        d_out = d_out.contiguous()
+        ws = scratch(x.device, L.query("ganffn_net_scratch_floats", *dims))
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        accumulate = 1 if arena.grads_live() else 0
+        L.call("ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
+               ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
+               spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, accumulate, _stream(x))
+        if not accumulate:
+            arena.install_grads()
+        ctx.stash = None
+        return dx, None, None, None, None, None, None, None
+
+
+def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Tensor, train: bool, p_head: float):
+    _require_cuda(x, "network input")
+    if x.dim() != 3:
+        raise ValueError(f"expected (seq_len, batch, dim) input, got shape {tuple(x.shape)}")
+    x = x.contiguous()
+    seed = next_seed() if train else 0
+    anchor = arena.flat
+    if arena.requires_grad and torch.is_grad_enabled():
+        anchor = arena.flat.detach().requires_grad_(True)  # makes autograd call backward even for data inputs
+    return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed)
+
+
+# --------------------------------------------------------------------------------------
+# fusion + classifier + log-softmax   (GAN_FFN.forward, model.py:1444-1449)
+# --------------------------------------------------------------------------------------
+class _FuseClsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, v, t, w, b):
+        L = lib()
+        S, B, dh = a.shape
+        C = w.shape[0]
+        T = S * B
+        a, v, t, w, b = a.contiguous(), v.contiguous(), t.contiguous(), w.contiguous(), b.contiguous()
+        fusion = torch.empty((S, B, dh), dtype=torch.float32, device=a.device)
+        logp = torch.empty((S, B, C), dtype=torch.float32, device=a.device)
+        L.call("ganffn_fuse_cls_fwd", ptr(a), ptr(v), ptr(t), ptr(w), ptr(b), ptr(fusion), ptr(logp), T, dh, C,
+               _stream(a))
+        ctx.save_for_backward(fusion, logp, w)
+        return logp
+
+    @staticmethod
+    def backward(ctx, d_logp):
+        L = lib()
+        fusion, logp, w = ctx.saved_tensors
+        S, B, dh = fusion.shape
+        C = w.shape[0]
+        T = S * B
+        d_logp = d_logp.contiguous()
+        d_fusion = torch.empty_like(fusion)
+        dw = torch.empty_like(w)
+        db = torch.empty(C, dtype=torch.float32, device=w.device)
+        ws = scratch(w.device, L.query("ganffn_fuse_cls_scratch_floats", T, dh, C), "cls")
+        L.call("ganffn_fuse_cls_bwd", ptr(d_logp), ptr(logp), ptr(fusion), ptr(w), ptr(d_fusion), ptr(dw), ptr(db), T,
+               dh, C, 0, ptr(ws), _stream(w))
+        return d_fusion, d_fusion, d_fusion, dw, db
+
+
+def fuse_classify(a, v, t, w, b):
+    for z in (a, v, t, w, b):
+        _require_cuda(z, "fuse_classify")
+    return _FuseClsFunction.apply(a, v, t, w, b)
+
+
+# --------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------
+class _MaskedNLLFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, weight, den_override: float):
+        L = lib()
+        n, C = pred.shape
+        pred = pred.contiguous()
+        out = torch.empty(2, dtype=torch.float32, device=pred.device)
+        L.call("ganffn_masked_nll_fwd", ptr(pred), ptr(target), ptr(mask), ptr(weight), ptr(out), n, C,
+               float(den_override), _stream(pred))
+        ctx.save_for_backward(target, mask)
+        ctx.out, ctx.weight, ctx.shape = out, weight, (n, C)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        L = lib()
+        target, mask = ctx.saved_tensors
+        out = ctx.out
+        n, C = ctx.shape
+        d_loss = d_loss.contiguous()
+        d_pred = torch.empty((n, C), dtype=torch.float32, device=out.device)
+        L.call("ganffn_masked_nll_bwd", ptr(d_loss), ptr(out), ptr(target), ptr(mask), ptr(ctx.weight), ptr(d_pred), n,
+               C, _stream(out))
+        return d_pred, None, None, None, None
+
+
+def masked_nll(pred, target, mask, weight=None, den_override: float = 0.0):
+    _require_cuda(pred, "MaskedNLLLoss pred")
+    if pred.dim() != 2:
+        raise ValueError(f"MaskedNLLLoss: pred must be (batch*seq_len, n_classes), got {tuple(pred.shape)}")
+    target = target.reshape(-1).to(torch.int64).contiguous()
+    mask = mask.reshape(-1).to(torch.float32).contiguous()
+    if target.numel() != pred.shape[0] or mask.numel() != pred.shape[0]:
+        raise ValueError("MaskedNLLLoss: pred, target and mask disagree on batch*seq_len")
+    if weight is not None:
+        weight = weight.to(device=pred.device, dtype=torch.float32).contiguous()
+    return _MaskedNLLFunction.apply(pred, target, mask, weight, den_override)
+
+
+class _BCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prob, target, scale: float):
+        L = lib()
+        prob, target = prob.contiguous(), target.contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=prob.device)
+        L.call("ganffn_bce_fwd", ptr(prob), ptr(target), ptr(out), prob.numel(), float(scale), _stream(prob))
+        ctx.save_for_backward(prob, target)
+        ctx.scale = scale
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        L = lib()
+        prob, target = ctx.saved_tensors
+        d_loss = d_loss.contiguous()
+        d_prob = torch.empty_like(prob)
+        L.call("ganffn_bce_bwd", ptr(d_loss), ptr(prob), ptr(target), ptr(d_prob), prob.numel(), float(ctx.scale),
+               _stream(prob))
+        return d_prob, None, None
+
+
+def bce(prob, target, scale: float = 1.0):
+    _require_cuda(prob, "BCELoss input")
+    if prob.shape != target.shape:
+        raise ValueError(f"BCELoss: input {tuple(prob.shape)} and target {tuple(target.shape)} differ")
+    target = target.to(device=prob.device, dtype=torch.float32)
+    return _BCEFunction.apply(prob, target, scale)
+
+
+# --------------------------------------------------------------------------------------
+# dropout-mask export (tests: inject the kernels' masks into the CPU oracle)
+# --------------------------------------------------------------------------------------
+def dropout_mask(rows: int, cols: int, p: float, seed: int, site: int, row_stride: Optional[int] = None,
+                 device="cuda") -> torch.Tensor:
+    out = torch.empty((rows, cols), dtype=torch.float32, device=device)
+    lib().call("ganffn_dropout_mask", ptr(out), rows, cols, cols if row_stride is None else row_stride, float(p),
+               seed, site, _stream(out))
+    return out

@@ -1,0 +1,97 @@
+"""Fused Adam over the flat parameter arenas.
+
+Same semantics as ``torch.optim.Adam`` as the reference uses it (train_IEMOCAP.py:292-297 and
+:661: L2 folded into the gradient, bias correction, eps outside the square root), but one
+kernel launch per network arena instead of a foreach over ~150 tensors, and a natural place for
+the data-parallel gradient all-reduce (one NCCL call per arena, see ``parallel.py``).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+
+from . import functional as GF
+from ._lib import lib, ptr
+
+
+def _arena_modules(module: torch.nn.Module):
+    from .model import _FusedNet
+    return [m for m in module.modules() if isinstance(m, _FusedNet)]
+
+
+class FusedAdam:
+    """``FusedAdam(module_or_modules, lr, betas, eps, weight_decay)``.
+
+    Parameters that live in a network arena are stepped with one ``ganffn_adam_step`` call per
+    arena; the few loose parameters (``GAN_FFN.fc``) get one call each.  Parameters whose
+    ``.grad`` is ``None`` (the reference's dead prototype layer, ``lstm``, ``smax_fc``) are
+    skipped, exactly as ``torch.optim.Adam`` skips them."""
+
+    def __init__(self, modules, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_reducer=None):
+        if isinstance(modules, torch.nn.Module):
+            modules = [modules]
+        self.modules: List[torch.nn.Module] = list(modules)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.grad_reducer = grad_reducer          # parallel.GradReducer or None
+        self.grad_scale = 1.0
+        self.state = {}                           # id(arena or param) -> dict(step, m, v)
+        self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
+
+    # -- discovery ------------------------------------------------------------------------
+    def _arenas(self):
+        seen, out = set(), []
+        for mod in self.modules:
+            for net in _arena_modules(mod):
+                ar = net.arena()
+                if id(ar) not in seen:
+                    seen.add(id(ar))
+                    out.append(ar)
+        return out
+
+    def _loose(self, arenas):
+        owned = {id(p) for ar in arenas for p in ar.params}
+        seen, out = set(), []
+        for mod in self.modules:
+            for p in mod.parameters():
+                if id(p) not in owned and id(p) not in seen and p.requires_grad:
+                    seen.add(id(p))
+                    out.append(p)
+        return out
+
+    # -- torch.optim API surface the reference loop uses ------------------------------------
+    def zero_grad(self, set_to_none: bool = True):
+        for mod in self.modules:
+            for p in mod.parameters():
+                if set_to_none:
+                    p.grad = None
+                elif p.grad is not None:
+                    p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        L = lib()
+        lr = self.param_groups[0]["lr"]
+        b1, b2 = self.betas
+        arenas = self._arenas()
+        live = [ar for ar in arenas if ar.grads_live()]
+        loose = [p for p in self._loose(arenas) if p.grad is not None]
+        if self.grad_reducer is not None:
+            self.grad_reducer.reduce([ar.grad for ar in live] + [p.grad for p in loose])
+        for ar in live:
+            st = self.state.get(id(ar))
+            if st is None:
+                st = {"step": 0, "m": torch.zeros_like(ar.flat), "v": torch.zeros_like(ar.flat), "keep": ar}
+                self.state[id(ar)] = st
+            st["step"] += 1
+            L.call("ganffn_adam_step", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel, st["step"],
+                   lr, b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(ar.flat))
+        for p in loose:
+            st = self.state.get(id(p))
+            if st is None:
+                st = {"step": 0, "m": torch.zeros_like(p), "v": torch.zeros_like(p), "keep": p}
+                self.state[id(p)] = st
+            st["step"] += 1
+            g = p.grad.contiguous()
+            L.call("ganffn_adam_step", ptr(p), ptr(g), ptr(st["m"]), ptr(st["v"]), p.numel(), st["step"], lr, b1, b2,
+                   self.eps, self.weight_decay, self.grad_scale, GF._stream(p))

@@ -1,0 +1,201 @@
+/*
+ * ganffn.h -- C ABI of the B200 (sm_100a) GAN-FFN fusion hot path.
+ *
+ * The reference (Jing-yilin/GAN-FFN) has no FFI of its own: its seam is the Python
+ * nn.Module surface of model.py.  Every entry point below therefore
+ * cites the reference *module code* it replaces; the Python host in gan_ffn_b200/
+ * keeps the reference's constructors and forward signatures and calls these through
+ * ctypes with raw device pointers (tensor.data_ptr()).
+ *
+ * Conventions
+ *  - All tensors are fp32, contiguous, device memory owned by the caller.
+ *  - Activations are seq-major (S,B,d) exactly as the reference feeds them
+ *    (model.py:1194), i.e. a row-major [T=S*B, d] matrix with row t = s*B + b.
+ *  - `stream` is a cudaStream_t passed as void*.  Nothing here allocates,
+ *    synchronises or throws.  Return value: GANFFN_OK or an error code;
+ *    ganffn_last_error() gives the text.
+ *  - Dropout: counter-based Philox4x32-10 keyed by (seed, site, element).  The same
+ *    (seed, site) regenerates the same mask in the backward pass; p == 0 is eval mode.
+ *    ganffn_dropout_mask() exports the mask a site draws so tests can inject it into
+ *    the CPU oracle.
+ */
+#ifndef GANFFN_H
+#define GANFFN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GANFFN_OK 0
+#define GANFFN_ERR_ARG 1   /* shape / pointer precondition violated */
+#define GANFFN_ERR_CUDA 2  /* a kernel launch failed */
+
+#define GANFFN_MAX_SEQ 110 /* PositionalEncoding(max_len=110), model.py:1179 */
+
+/* dropout sites (shared with oracle/ganffn_oracle.py) */
+#define GANFFN_SITE_PE 0
+#define GANFFN_SITE_LAYER(l, k) (16 * ((l) + 1) + (k)) /* k: 0 attn P, 1 out-proj, 2 FFN hidden, 3 linear2 */
+#define GANFFN_SITE_HEAD 200                            /* +0 gelu(enc) [gen], +1 fc1, +2 fc2, +3 fc3 */
+
+/* activation codes for ganffn_linear_fwd */
+#define GANFFN_ACT_NONE 0
+#define GANFFN_ACT_RELU 1
+#define GANFFN_ACT_GELU 2
+#define GANFFN_ACT_SIGMOID 3
+
+/* network kinds for the whole-network entry points */
+#define GANFFN_NET_GENERATOR 0     /* model.py:1200-1294 */
+#define GANFFN_NET_DISCRIMINATOR 1 /* model.py:1297-1397 */
+
+/* GEMM engines */
+#define GANFFN_GEMM_AUTO 0
+#define GANFFN_GEMM_SIMT 1   /* fp32 FFMA tiles */
+#define GANFFN_GEMM_TC 2     /* tcgen05 kind::tf32, 3xTF32 error-compensated */
+
+/* ---- library state -------------------------------------------------------------------- */
+int ganffn_version(void);
+const char* ganffn_last_error(void);
+/* Number of kernels this library has launched since load / last reset (bench.py: gpu_launches). */
+unsigned long long ganffn_launch_count(void);
+void ganffn_reset_launch_count(void);
+/* Select the GEMM engine (GANFFN_GEMM_*); returns the previous value. */
+int ganffn_set_gemm_engine(int engine);
+
+/* ---- primitives (each is also used by the whole-network calls) ------------------------ */
+
+/* y[M,N] = epilogue(x[M,K] @ w[N,K]^T + bias).  Replaces nn.Linear inside
+ * TransformerEncoderLayer (torch transformer.py:961-982) and fc1/fc2/fc3/object/fc
+ * (model.py:1214-1215, 1311-1313, 1344, 1432).
+ *   drop_before_act = 1: y = act(drop(v))  (heads, model.py:1227-1228, 1324-1326)
+ *   drop_before_act = 0: y = drop(act(v))  (FFN hidden, transformer.py:981)
+ *   residual (optional) is added last; pre (optional) receives the value fed to act. */
+int ganffn_linear_fwd(const float* x, const float* w, const float* bias, const float* residual,
+                      float* y, float* pre, int M, int N, int K, int act, int drop_before_act,
+                      float p_drop, uint64_t seed, int site, float* scratch,
+                      int64_t scratch_floats, void* stream);
+/* Split-K workspace (floats) the GEMM engines want for an [M,N,K] product; may be 0. */
+int64_t ganffn_gemm_scratch_floats(int M, int N, int K);
+
+/* dx[M,K] = dy[M,N] @ w[N,K] (+ residual[M,K]).  Backward-data of nn.Linear. */
+int ganffn_linear_dgrad(const float* dy, const float* w, const float* residual, float* dx,
+                        int M, int N, int K, float* scratch, int64_t scratch_floats,
+                        void* stream);
+
+/* dw[N,K] (+)= dy[M,N]^T @ x[M,K]; db[N] (+)= column sums of dy.  Backward-weight of
+ * nn.Linear.  accumulate != 0 adds into dw/db.  scratch: >= ganffn_wgrad_scratch_floats(). */
+int ganffn_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int N, int K,
+                        int accumulate, float* scratch, void* stream);
+int64_t ganffn_wgrad_scratch_floats(int M, int N, int K);
+
+/* Self-attention core for all (dialogue, head) pairs: o = softmax(q k^T / sqrt(hd)) v with
+ * dropout on the probabilities.  qkv is the packed in-proj output [T, 3d]; o is [T, d];
+ * lse [B*nhead*S] receives the row log-sum-exp for the backward pass.
+ * Replaces F.scaled_dot_product_attention inside nn.MultiheadAttention
+ * (torch functional.py multi_head_attention_forward). */
+int ganffn_attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead,
+                         float p_drop, uint64_t seed, int site, void* stream);
+int ganffn_attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o,
+                         float* dqkv, int S, int B, int d, int nhead, float p_drop, uint64_t seed,
+                         int site, void* stream);
+
+/* y = LayerNorm(z) (eps 1e-5, torch default).  z already holds x + sublayer(x). */
+int ganffn_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T,
+                         int d, void* stream);
+/* dz = LN backward; dz_drop (optional) = dz * dropout_mask(site) for the sublayer branch;
+ * dgamma/dbeta (+)= reductions.  scratch: >= ganffn_layernorm_scratch_floats(). */
+int ganffn_layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz,
+                         float* dz_drop, float* dgamma, float* dbeta, int T, int d, int accumulate,
+                         float p_drop, uint64_t seed, int site, float* scratch, void* stream);
+int64_t ganffn_layernorm_scratch_floats(int T, int d);
+
+/* y[s,b,:] = drop(x[s,b,:] + pe[s,:])  (PositionalEncoding.forward, model.py:1191-1197).
+ * pe is the module's registered buffer viewed as [max_len, d] (model.py:1186-1189). */
+int ganffn_posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p_drop,
+                      uint64_t seed, void* stream);
+
+/* Writes out[rows,cols] = the scaled keep mask (0 or 1/(1-p)) that `site` draws; element (r,c)
+ * is Philox element r*row_stride + c.  row_stride == cols for every [T,N] site; the attention
+ * site uses rows = B*nhead*S, cols = S, row_stride = round_up(S,4). */
+int ganffn_dropout_mask(float* out, int64_t rows, int64_t cols, int64_t row_stride, float p_drop,
+                        uint64_t seed, int site, void* stream);
+
+/* ---- losses ---------------------------------------------------------------------------- */
+/* log_prob[T,C] = log_softmax((a+v+t) @ w[C,100]^T + b)  (GAN_FFN.forward, model.py:1444-1449).
+ * fusion[T,dh] (optional) receives a+v+t (GAN_FFN_DialogueRNN.forward, model.py:1524). */
+int ganffn_fuse_cls_fwd(const float* a, const float* v, const float* t, const float* w,
+                        const float* b, float* fusion, float* log_prob, int T, int dh, int C,
+                        void* stream);
+/* Given d_log_prob: d_fusion[T,dh] (same for a, v and t), dw[C,dh] (+)=, db[C] (+)=. */
+int ganffn_fuse_cls_bwd(const float* d_log_prob, const float* log_prob, const float* fusion,
+                        const float* w, float* d_fusion, float* dw, float* db, int T, int dh, int C,
+                        int accumulate, float* scratch, void* stream);
+int64_t ganffn_fuse_cls_scratch_floats(int T, int dh, int C);
+
+/* MaskedNLLLoss.forward (model.py:68-81): pred [n,C] log-probs, target int64 [n], mask [n],
+ * weight [C] or NULL.  loss_and_den[0] = loss, [1] = denominator sum(w[t]*m).
+ * `den_override` > 0 replaces the denominator (global denominator under dialogue sharding). */
+int ganffn_masked_nll_fwd(const float* pred, const int64_t* target, const float* mask,
+                          const float* weight, float* loss_and_den, int64_t n, int C,
+                          float den_override, void* stream);
+int ganffn_masked_nll_bwd(const float* d_loss, const float* loss_and_den, const int64_t* target,
+                          const float* mask, const float* weight, float* d_pred, int64_t n, int C,
+                          void* stream);
+
+/* torch.nn.BCELoss() (train_IEMOCAP.py:300): mean over n of -[y log p + (1-y) log(1-p)], logs
+ * clamped at -100.  `scale` multiplies the mean (1/world_size under dialogue sharding). */
+int ganffn_bce_fwd(const float* prob, const float* target, float* loss, int64_t n, float scale,
+                   void* stream);
+int ganffn_bce_bwd(const float* d_loss, const float* prob, const float* target, float* d_prob,
+                   int64_t n, float scale, void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------- */
+/* torch.optim.Adam over one flat parameter arena (train_IEMOCAP.py:292-297, :661): L2 term
+ * folded into the gradient, bias-corrected, eps outside the sqrt.  `step` is 1-based.
+ * grad_scale multiplies g first (1/world_size after a sum-allreduce). */
+int ganffn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                     void* stream);
+
+/* ---- whole networks -------------------------------------------------------------------- */
+/* One generator / discriminator forward: [object] -> PE -> nlayers x encoder layer -> head.
+ *   params      flat fp32 arena; off[] gives each tensor's float offset in canonical order:
+ *               per layer l (12 entries): in_proj_weight, in_proj_bias, out_proj.weight,
+ *               out_proj.bias, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
+ *               norm1.weight, norm1.bias, norm2.weight, norm2.bias; then head entries:
+ *               generator: fc1.w, fc1.b, fc2.w, fc2.b;
+ *               discriminator: fc1.w, fc1.b, fc2.w, fc2.b, fc3.w, fc3.b, object.w, object.b
+ *               (object.* = -1 when absent).
+ *   x           (S,B,d_in); d_in == d, or 512 with d == 100 for the visual discriminator's
+ *               real input (model.py:1355-1356).
+ *   pe          the PositionalEncoding buffer viewed as [max_len, d].
+ *   h1, h2      head widths: generator fc1 d->h1, fc2 h1->h2 (= D_h); discriminator fc1 d->h1 (64),
+ *               fc2 h1->h2 (16), fc3 h2->1.
+ *   out         generator: (S,B,h2) fused feature; discriminator: (S,B,1) probability.
+ *   stash       activation stash for the backward pass, ganffn_net_stash_floats() floats.
+ *   scratch     ganffn_net_scratch_floats() floats of workspace (split-K partials etc.).
+ *   p_scale     0 = eval mode (all dropout off); 1 = train mode (reference probabilities:
+ *               PE 0.2, encoder 0.1, head `p_head`).
+ * Replaces model.py:1221-1231, 1255-1263, 1286-1294, 1320-1327, 1354-1364, 1390-1397. */
+int ganffn_net_fwd(int kind, const float* params, const int64_t* off, const float* pe,
+                   const float* x, float* out, float* stash, float* scratch, int S, int B, int d_in,
+                   int d, int nhead, int dff, int nlayers, int h1, int h2, int train, float p_head,
+                   uint64_t seed, void* stream);
+/* Backward of the above.  grads has the arena's layout; accumulate != 0 adds into it.
+ * dx may be NULL when the input needs no gradient.  scratch: ganffn_net_scratch_floats(). */
+int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const float* x,
+                   const float* out, const float* d_out_grad, const float* stash, float* grads,
+                   float* dx, float* scratch, int S, int B, int d_in, int d, int nhead, int dff,
+                   int nlayers, int h1, int h2, int train, float p_head, uint64_t seed,
+                   int accumulate, void* stream);
+/* Both return -1 when the shape violates a precondition (ganffn_last_error() says which). */
+int64_t ganffn_net_stash_floats(int kind, int S, int B, int d_in, int d, int nhead, int dff,
+                                int nlayers, int h1, int h2);
+int64_t ganffn_net_scratch_floats(int kind, int S, int B, int d_in, int d, int nhead, int dff,
+                                  int nlayers, int h1, int h2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANFFN_H */
