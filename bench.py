@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- GAN-FFN train-step throughput (utterances/s) on 1..8 B200.
+
+A *step* is one pass of the whole hot path over one IEMOCAP-shaped synthetic batch per GPU
+(S=94 turns x B=32 dialogues, text/visual/acoustic 100/512/100, 6 classes, train mode, dropout on):
+  stage 1  the twelve adversarial sub-steps of reference train_IEMOCAP.py:355-382
+           (6x train_disc + 6x train_gen: generator and discriminator fwd/bwd, BCE, Adam), then
+  stage 2  one classifier step of train_IEMOCAP.py:127-170 (GAN_FFN fwd, MaskedNLLLoss, bwd, Adam).
+Unit of work: padded utterance slots S*B (all are computed and, in stage 1, all enter the loss).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (torchrun for N>1)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S_IEMOCAP, B_IEMOCAP = 94, 32
+METRIC = "gan_ffn_train_step_padded_utterances_per_sec"
+UNIT = "utterances/s"
+WORKLOAD = "iemocap_train_step: stage-1 GAN batch (12 sub-steps) + stage-2 classifier step, S=94 B=32 per GPU, fp32, dropout on"
+
+
+def flops_per_slot(S):
+    """Algorithmic FLOP per padded slot: stage-1 batch + stage-2 step."""
+    E = lambda d: 8 * d * d + 4 * S * d + 8192 * d
+    G = lambda d, h: 8 * E(d) + 2 * d * h + 200 * h
+    D = 8 * E(100) + 14880
+    ffn_fwd = 2 * G(100, 512) + G(512, 1024) + 1200
+    stage2 = 3 * ffn_fwd
+    g100, g512 = G(100, 512), G(512, 1024)
+    # train_disc: D(real) + G fwd (eval) + D(fake) fwd, bwd through both D passes (2x fwd each)
+    # train_gen: G fwd + D fwd, bwd through both
+    def disc_step(gf, real_extra):
+        return (2 * D + real_extra + gf) + 2 * (2 * D + real_extra)
+    def gen_step(gf):
+        return 3 * (gf + D)
+    obj = 102400
+    stage1 = (disc_step(g100, obj) + gen_step(g100)) * 2 + (disc_step(g100, 0) + gen_step(g100)) * 2 \
+        + (disc_step(g512, 0) + gen_step(g512)) * 2
+    return stage1, stage2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle/reference_port.py: stock torch modules, the
+    reference's own operators and loop bodies) on the box's host cores.  Each step is a bounded sample of the
+    workload: `--ref-dialogues` dialogues (default 4 of the 32) at the same S=94, so the run ends in minutes."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gan_ffn_b200 import synthetic
+    from oracle import reference_port as RP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nets, ffn = RP.build()
+    tr = RP.PortTrainer(nets, ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS))
+    # bounded sample: CPU step time here is ~1.9 s fixed (Adam, weight traffic) + ~1.0 s per dialogue; pick the
+    # largest dialogue count (<= 32) that keeps warm-up + K steps within ~4 minutes.
+    warm = min(args.warmup, 1)
+    nd = args.ref_dialogues or int(max(2, min(B_IEMOCAP, (240.0 / (args.steps + warm) - 1.9) / 1.0)))
+    b = synthetic.make_batch(n_dialogues=nd, seq_len=S_IEMOCAP)
+    def step():
+        tr.gan_batch(b)
+        tr.classifier_step(b)
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    slots = b.padded_slots
+    val = slots * args.steps / dt
+    sample = f"{nd} of {B_IEMOCAP} dialogues at S={S_IEMOCAP} ({slots} padded slots/step), {warm} warm-up + {args.steps} steps, dropout on"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample, "torch": torch.__version__},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(seconds_budget=25.0):
+    """The oracle port timed on the host cores on a bounded sample (rank 0, N=1 only)."""
+    import torch
+    from gan_ffn_b200 import synthetic
+    from oracle import reference_port as RP
+    cores = os.cpu_count() or 1
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    try:
+        nets, ffn = RP.build()
+        tr = RP.PortTrainer(nets, ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS))
+        nd = 4
+        b = synthetic.make_batch(n_dialogues=nd, seq_len=S_IEMOCAP)
+        tr.gan_batch(b); tr.classifier_step(b)           # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            tr.gan_batch(b); tr.classifier_step(b)
+            n += 1
+            if time.perf_counter() - t0 > seconds_budget * 0.5 or n >= 2:
+                break
+        dt = time.perf_counter() - t0
+        return {"value": b.padded_slots * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n} steps of {nd} of {B_IEMOCAP} dialogues at S={S_IEMOCAP} ({b.padded_slots} slots/step), dropout on, torch {torch.__version__} CPU"}
+    finally:
+        torch.set_num_threads(prev)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gan_ffn_b200 as G
+    from gan_ffn_b200 import parallel, synthetic, train
+    from gan_ffn_b200._lib import lib
+    import ctypes
+
+    rank, local_rank, world = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm"
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = lib()
+    if args.engine is not None:
+        L.cdll.ganffn_set_gemm_engine({"auto": 0, "simt": 1, "tc": 2}[args.engine])
+
+    reducer = parallel.GradReducer() if world > 1 else None
+    nets, ffn = train.build_networks(device=dev)
+    gan = train.GANTrainer(nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], nets["acoustic_disc"],
+                           nets["visual_disc"], nets["text_disc"], grad_reducer=reducer, world_size=world)
+    cls = train.ClassifierTrainer(ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev), grad_reducer=reducer)
+    G.manual_seed(3407 + rank)
+
+    S, B = args.seq_len, args.dialogues
+    host = synthetic.make_batch(n_dialogues=B, seq_len=S, seed=3407 + rank).pin()   # weak scaling: fixed work per GPU
+    resident = host.to(dev)
+
+    def step(batch):
+        losses = gan.batch(batch)
+        loss, pred, _ = cls.step(batch, train=True)
+        return losses, loss, pred
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    # ---- warm-up -------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 0)):
+        step(resident)
+    barrier()
+
+    # ---- timed region: K steps, CUDA events per step on the launching stream, L2 flushed in between --------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    L.cdll.ganffn_reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b_ in ev:
+        flush.zero_()
+        a.record()
+        step(resident)
+        b_.record()
+    barrier()
+    launches = int(L.cdll.ganffn_launch_count())
+    ms_total = sum(a.elapsed_time(b_) for a, b_ in ev)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    slots = S * B * world
+    value = slots * args.steps / (ms_total / 1e3)
+
+    # ---- stage split (untimed for the headline; reported in config) --------------------------------------------
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    barrier()
+    e0.record(); gan.batch(resident); e1.record(); cls.step(resident, train=True); e2.record()
+    barrier()
+    stage1_ms, stage2_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+
+    # ---- end to end: pinned host batch -> device every step, losses and predictions read back -----------------
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        db = host.to(dev, non_blocking=True)
+        losses, loss, pred = step(db)
+        vals = torch.stack([losses[k] for k in sorted(losses)] + [loss]).cpu()      # 7 scalars
+        pred_host = pred.cpu()
+        d2h = vals.numel() * 4 + pred_host.numel() * pred_host.element_size()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = slots * args.steps / float(t.item())
+
+    # ---- roofline leg: per-GEMM CUDA events over one more step ------------------------------------------------------
+    L.cdll.ganffn_gemm_profile_enable(1)
+    step(resident)
+    torch.cuda.synchronize()
+    L.cdll.ganffn_gemm_profile_enable(0)
+    ms_a, fl_a, n_a = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    L.call("ganffn_gemm_profile_collect", 0, ctypes.byref(ms_a), ctypes.byref(fl_a), ctypes.byref(n_a))
+    gemm_ms, gemm_flops, gemm_n = ms_a.value, fl_a.value, n_a.value
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    s1, s2 = flops_per_slot(S)
+    roofline = {"bound": "tensor", "kernel": "GEMM engine (all linear layers fwd/dgrad/wgrad incl. split-K fold)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
+                "traffic": traffic, "peak_source": peak_src, "launches_per_step": gemm_n,
+                "avg_launch_us": 1e3 * gemm_ms / gemm_n if gemm_n else None,
+                "algorithmic_gflop_per_launch": gemm_flops / gemm_n / 1e9 if gemm_n else None,
+                "gemm_share_of_step": gemm_ms / (ms_total / args.steps) if ms_total else None,
+                "note": "fp32-parity arithmetic: FFMA tiles or 3xTF32 tcgen05 (3 MMAs per product at half the bf16 rate), so frac <= ~0.17 by construction against the bf16 peak"}
+
+    if rank == 0:
+        cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD if (S, B) == (S_IEMOCAP, B_IEMOCAP) else f"train_step S={S} B={B} per GPU",
+                           "seq_len": S, "dialogues_per_gpu": B, "global_dialogues": B * world, "parallelism": f"dp{world} by dialogue",
+                           "stage1_ms": stage1_ms, "stage2_ms": stage2_ms,
+                           "algorithmic_gflop_per_step_per_gpu": (s1 + s2) * S * B / 1e9,
+                           "step_tflops_per_gpu": (s1 + s2) * S * B / (ms_total / args.steps / 1e3) / 1e12,
+                           "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set ~2 GB >> 126 MB L2",
+                           "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
+                           "gemm_engine": args.engine or "auto"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(), "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches,
+                "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seq-len", type=int, default=S_IEMOCAP)
+    ap.add_argument("--dialogues", type=int, default=B_IEMOCAP, help="dialogues per GPU")
+    ap.add_argument("--ref-dialogues", type=int, default=0, help="dialogues per step of the CPU reference arm (0 = fit ~4 min)")
+    ap.add_argument("--engine", default=None, choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,7 @@ _CTYPES = {
     "uint64_t": ctypes.c_uint64,
     "float": ctypes.c_float,
     "unsigned long long": ctypes.c_ulonglong,
+    "double": ctypes.c_double,
     "void": None,
 }
 

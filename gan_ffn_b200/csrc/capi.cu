@@ -2,6 +2,8 @@
 // dispatcher.
 #include <stdarg.h>
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "kernels.h"
 
@@ -26,11 +28,39 @@ static bool use_tc(bool transA, bool b_is_nk, int lda, int ldb, int ldc, int M, 
   return gemm_tc_supported(transA, b_is_nk, lda, ldb, ldc, M, N, K, A, B);
 }
 
+// ---- per-GEMM CUDA-event profiling (bench.py roofline leg) ------------------------------------------------
+// When enabled, every GEMM (including its split-K fold) is bracketed by two events on the launching
+// stream; ganffn_gemm_profile_collect() synchronises and sums elapsed time and algorithmic FLOPs per engine.
+struct ProfEntry { cudaEvent_t a, b; double flops; int engine; };
+static bool g_prof = false;
+static std::vector<ProfEntry> g_prof_entries;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+
+static ProfEntry prof_begin(double flops, int engine, cudaStream_t st) {
+  ProfEntry e;
+  if (!g_prof_pool.empty()) {
+    e.a = g_prof_pool.back().first; e.b = g_prof_pool.back().second;
+    g_prof_pool.pop_back();
+  } else {
+    cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+  }
+  e.flops = flops; e.engine = engine;
+  cudaEventRecord(e.a, st);
+  return e;
+}
+
 int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
          int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st) {
-  if (use_tc(transA, b_is_nk, lda, ldb, ldc, M, N, K, A, B))
-    return gemm_tc(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
-  return gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
+  const bool tc = use_tc(transA, b_is_nk, lda, ldb, ldc, M, N, K, A, B);
+  ProfEntry pe{};
+  if (g_prof) pe = prof_begin(2.0 * M * N * K, tc ? GANFFN_GEMM_TC : GANFFN_GEMM_SIMT, st);
+  const int rc = tc ? gemm_tc(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st)
+                    : gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
+  if (g_prof) {
+    cudaEventRecord(pe.b, st);
+    g_prof_entries.push_back(pe);
+  }
+  return rc;
 }
 
 int64_t gemm_scratch_floats(int M, int N, int K) {
@@ -49,6 +79,22 @@ int ganffn_version(void) { return 100; }
 const char* ganffn_last_error(void) { return g_err; }
 unsigned long long ganffn_launch_count(void) { return g_launches; }
 void ganffn_reset_launch_count(void) { g_launches = 0; }
+void ganffn_gemm_profile_enable(int on) { g_prof = on != 0; }
+int ganffn_gemm_profile_collect(int engine, double* total_ms, double* total_flops, int64_t* launches) {
+  GANFFN_CHECK_ARG(total_ms && total_flops && launches, "gemm_profile_collect: null pointer");
+  double ms = 0.0, fl = 0.0;
+  int64_t n = 0;
+  for (auto& e : g_prof_entries) {
+    if (cudaEventSynchronize(e.b) != cudaSuccess) { set_error("gemm_profile_collect: event sync failed"); return GANFFN_ERR_CUDA; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e.a, e.b);
+    if (engine == GANFFN_GEMM_AUTO || engine == e.engine) { ms += t; fl += e.flops; ++n; }
+    g_prof_pool.emplace_back(e.a, e.b);
+  }
+  g_prof_entries.clear();
+  *total_ms = ms; *total_flops = fl; *launches = n;
+  return GANFFN_OK;
+}
 int ganffn_set_gemm_engine(int engine) {
   int prev = g_gemm_engine;
   if (engine >= GANFFN_GEMM_AUTO && engine <= GANFFN_GEMM_TC) g_gemm_engine = engine;

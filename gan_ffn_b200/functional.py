@@ -166,6 +166,11 @@ class _NetFunction(torch.autograd.Function):
                ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
                spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, accumulate, _stream(x))
         if not accumulate:
+            if spec.kind == 1 and d_in == spec.d and arena.table[-1] >= 0:
+                # visual discriminator fed a D_h-wide (generated) input: `object` was bypassed
+                # (reference model.py:1355), so its gradient for this pass is zero, not stale.
+                arena.grad_views[-1].zero_()
+                arena.grad_views[-2].zero_()
             arena.install_grads()
         ctx.stash = None
         return dx, None, None, None, None, None, None, None

@@ -1,0 +1,82 @@
+"""Data parallelism by dialogue.
+
+One process per GPU.  A global batch of dialogues is split along dim 1 of ``(S,B,d)`` -- never
+along the sequence axis, which is what the reference's ``nn.DataParallel(dim=0)`` does by accident
+(train_IEMOCAP.py:587-593, README.md:82-83) -- and every shard keeps the *global* pad length,
+because a dialogue's output depends on how far it is zero-padded.  Gradients are
+summed with one all-reduce per parameter arena per optimizer step (NCCL over NVLink on GPUs, gloo
+in the CPU tests); losses are scaled so that the summed shard gradients equal the single-device
+gradient on the whole global batch:
+
+  * BCELoss is a mean over all S*B slots  -> each rank uses local_mean / world_size;
+  * MaskedNLLLoss divides by sum(w[label]*umask) -> every rank divides by the *global* sum.
+
+Inference scoring needs no collective at all.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .synthetic import Batch
+
+
+def shard_indices(n_dialogues: int, world_size: int, rank: int) -> List[int]:
+    """Contiguous, balanced split of dialogue indices (first ``n % world`` ranks get one more)."""
+    base, rem = divmod(n_dialogues, world_size)
+    start = rank * base + min(rank, rem)
+    return list(range(start, start + base + (1 if rank < rem else 0)))
+
+
+def shard_batch(batch: Batch, world_size: int, rank: int) -> Batch:
+    """This rank's dialogues of a global batch, padded to the global seq_len."""
+    return batch.dialogues(shard_indices(batch.n_dialogues, world_size, rank))
+
+
+class GradReducer:
+    """Sum-all-reduce of flat gradient buffers across the data-parallel group."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("GradReducer needs torch.distributed to be initialised (one process per GPU)")
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.bytes_reduced = 0
+        self.calls = 0
+
+    def reduce(self, buffers: Sequence[torch.Tensor]) -> None:
+        works = []
+        for b in buffers:
+            works.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.bytes_reduced += b.numel() * b.element_size()
+            self.calls += 1
+        for w in works:
+            w.wait()
+
+    def global_nll_denominator(self, label: torch.Tensor, umask: torch.Tensor, weight: Optional[torch.Tensor]) -> float:
+        """sum over the *global* batch of w[label]*umask (MaskedNLLLoss denominator, model.py:78-80)."""
+        m = umask.reshape(-1).to(torch.float32)
+        w = m if weight is None else weight.to(m.device)[label.reshape(-1)] * m
+        den = w.sum().reshape(1)
+        dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
+        return float(den.item())
+
+
+def init_from_env(backend: Optional[str] = None):
+    """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns
+    (rank, local_rank, world_size)."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world

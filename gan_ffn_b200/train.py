@@ -1,0 +1,145 @@
+"""The reference's two training loops, bodies unchanged, over our modules.
+
+``train_disc`` / ``train_gen`` / ``gan_batch`` restate reference train_IEMOCAP.py:200-252 and the
+twelve pairings of :355-382; ``classifier_step`` restates the body of ``train_or_eval_model``
+(:127-170).  Only the constructors differ from the reference scripts: the loss modules are
+``gan_ffn_b200.BCELoss`` / ``MaskedNLLLoss`` and the optimizers ``gan_ffn_b200.FusedAdam``
+(same hyper-parameters: train_IEMOCAP.py:292-297, :602-606, :661).
+
+The reference's ``.type(torch.FloatTensor)`` round trip that sends the stage-1 inputs back to the CPU
+(train_IEMOCAP.py:349-351, :40) is a bug of the script, not part of the arithmetic, and is not
+reproduced: batches stay device-resident.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import model as M
+from .optim import FusedAdam
+from .synthetic import Batch
+
+GAN_LR, GAN_B1, GAN_B2 = 1e-4, 0.5, 0.6          # train_IEMOCAP.py:602-606
+FFN_LR, FFN_L2 = 1e-4, 0.008                     # train_IEMOCAP.py:456-457 (--lr, --l2 defaults)
+
+
+def train_disc(disc, real_dics, gen, real_gen, opt, adversarial_loss, valid, fake):
+    """reference train_IEMOCAP.py:200-227."""
+    disc.train()
+    gen.eval()
+
+    opt.zero_grad()
+    real_prob = disc(real_dics)
+    fusion = gen(real_gen)
+    fake_prob = disc(fusion.detach())
+    d_loss = (adversarial_loss(real_prob, valid) + adversarial_loss(fake_prob, fake)) / 2.0
+    res = d_loss.detach()
+    d_loss.backward()
+    opt.step()
+    return res
+
+
+def train_gen(gen, real_gen, disc, opt, adversarial_loss, valid, fake):
+    """reference train_IEMOCAP.py:230-252."""
+    gen.train()
+    disc.eval()
+
+    opt.zero_grad()
+    fusion = gen(real_gen)
+    prob = disc(fusion)
+    g_loss = adversarial_loss(prob, valid)
+    res = g_loss.detach()
+    g_loss.backward()
+    opt.step()
+    return res
+
+
+class GANTrainer:
+    """Stage 1 (reference ``train_GAN``, train_IEMOCAP.py:255-393): six networks, six Adam
+    optimizers (generators lr, discriminators lr/2, text generator lr*1.1), BCE adversarial loss."""
+
+    def __init__(self, acoustic_gen, visual_gen, text_gen, acoustic_disc, visual_disc, text_disc, lr=GAN_LR, b1=GAN_B1,
+                 b2=GAN_B2, grad_reducer=None, world_size: int = 1):
+        self.nets = dict(acoustic_gen=acoustic_gen, visual_gen=visual_gen, text_gen=text_gen, acoustic_disc=acoustic_disc,
+                         visual_disc=visual_disc, text_disc=text_disc)
+        mk = lambda net, rate: FusedAdam(net, lr=rate, betas=(b1, b2), grad_reducer=grad_reducer)
+        self.opt_acoustic_G = mk(acoustic_gen, lr)
+        self.opt_acoustic_D = mk(acoustic_disc, lr / 2)
+        self.opt_visual_G = mk(visual_gen, lr)
+        self.opt_visual_D = mk(visual_disc, lr / 2)
+        self.opt_text_G = mk(text_gen, lr * 1.1)
+        self.opt_text_D = mk(text_disc, lr / 2)
+        self.adversarial_loss = M.BCELoss()
+        self.adversarial_loss.scale = 1.0 / world_size   # mean over the *global* S*B under dialogue sharding
+
+    def batch(self, data: Batch) -> Dict[str, torch.Tensor]:
+        """The twelve sub-steps of one batch, in the reference's order (train_IEMOCAP.py:355-382).
+        Returns the six surviving loss values as device scalars (later sub-steps overwrite earlier ones,
+        as in the reference)."""
+        n = self.nets
+        real_text, real_visual, real_acoustic = data.text, data.visual, data.acoustic
+        seq_len, batch_size = real_text.size(0), real_text.size(1)
+        valid = torch.ones(seq_len, batch_size, 1, device=real_text.device)
+        fake = torch.zeros(seq_len, batch_size, 1, device=real_text.device)
+        adv = self.adversarial_loss
+        loss = {}
+        loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["acoustic_gen"], real_acoustic, self.opt_visual_D, adv, valid, fake)
+        loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["visual_disc"], self.opt_acoustic_G, adv, valid, fake)
+        loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["text_gen"], real_text, self.opt_visual_D, adv, valid, fake)
+        loss["text_G_loss"] = train_gen(n["text_gen"], real_text, n["visual_disc"], self.opt_text_G, adv, valid, fake)
+        loss["text_D_loss"] = train_disc(n["text_disc"], real_text, n["acoustic_gen"], real_acoustic, self.opt_text_D, adv, valid, fake)
+        loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["text_disc"], self.opt_acoustic_G, adv, valid, fake)
+        loss["acoustic_D_loss"] = train_disc(n["acoustic_disc"], real_acoustic, n["text_gen"], real_text, self.opt_acoustic_D, adv, valid, fake)
+        loss["text_G_loss"] = train_gen(n["text_gen"], real_text, n["acoustic_disc"], self.opt_text_G, adv, valid, fake)
+        loss["text_D_loss"] = train_disc(n["text_disc"], real_text, n["visual_gen"], real_visual, self.opt_text_D, adv, valid, fake)
+        loss["visual_G_loss"] = train_gen(n["visual_gen"], real_visual, n["text_disc"], self.opt_visual_G, adv, valid, fake)
+        loss["acoustic_D_loss"] = train_disc(n["acoustic_disc"], real_acoustic, n["visual_gen"], real_visual, self.opt_acoustic_D, adv, valid, fake)
+        loss["visual_G_loss"] = train_gen(n["visual_gen"], real_visual, n["acoustic_disc"], self.opt_visual_G, adv, valid, fake)
+        return loss
+
+
+class ClassifierTrainer:
+    """Stage 2 (reference ``train_or_eval_model``, train_IEMOCAP.py:103-197) for ``GAN_FFN``."""
+
+    def __init__(self, model: M.GAN_FFN, loss_weights=None, lr=FFN_LR, l2=FFN_L2, grad_reducer=None):
+        self.model = model
+        self.loss_function = M.MaskedNLLLoss(loss_weights)
+        self.optimizer = FusedAdam(model, lr=lr, weight_decay=l2, grad_reducer=grad_reducer)
+        self.grad_reducer = grad_reducer
+
+    def step(self, data: Batch, train: bool = True):
+        """One batch of the loop body (train_IEMOCAP.py:127-170).  Returns (loss, pred_, labels_)."""
+        model, optimizer = self.model, self.optimizer
+        model.train() if train else model.eval()
+        if train:
+            optimizer.zero_grad()
+        textf, visuf, acouf, umask, label = data.text, data.visual, data.acoustic, data.umask, data.label
+        if self.grad_reducer is not None and train:
+            # global denominator sum(w[label]*umask) so that summed shard gradients equal the
+            # single-device gradient on the whole batch
+            self.loss_function.den_override = self.grad_reducer.global_nll_denominator(label, umask, self.loss_function.weight)
+        with torch.set_grad_enabled(train):
+            log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf)
+            lp_ = log_prob.transpose(0, 1).contiguous().view(-1, log_prob.size()[2])
+            labels_ = label.view(-1)
+            loss = self.loss_function(lp_, labels_, umask)
+        pred_ = torch.argmax(lp_, 1)
+        if train:
+            loss.backward()
+            optimizer.step()
+        return loss.detach(), pred_, labels_
+
+
+def build_networks(D_h: int = 100, n_classes: int = 6, device="cuda", seed: int = 3407):
+    """The six networks + GAN_FFN as the reference's ``__main__`` builds them
+    (train_IEMOCAP.py:580-585, :629-635: GAN dropout 0.2, GAN_FFN dropout --dropout 0.6)."""
+    torch.manual_seed(seed)
+    nets = dict(acoustic_gen=M.AcousticGenerator(D_h, dropout=0.2), acoustic_disc=M.AcousticDiscriminator(D_h, dropout=0.2),
+                visual_gen=M.VisualGenerator(D_h, dropout=0.2), visual_disc=M.VisualDiscriminator(D_h, dropout=0.2),
+                text_gen=M.TextGenerator(D_h, dropout=0.2), text_disc=M.TextDiscriminator(D_h, dropout=0.2))
+    ffn = M.GAN_FFN(nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], n_classes=n_classes, dropout=0.6)
+    ffn.to(device)
+    for k in ("acoustic_disc", "visual_disc", "text_disc"):
+        nets[k].to(device)
+    return nets, ffn

@@ -63,6 +63,13 @@ void ganffn_reset_launch_count(void);
 /* Select the GEMM engine (GANFFN_GEMM_*); returns the previous value. */
 int ganffn_set_gemm_engine(int engine);
 
+/* GEMM profiling for the roofline leg of bench.py: when enabled every GEMM (with its split-K
+ * fold) is bracketed by CUDA events on the launching stream.  collect() synchronises, sums the
+ * elapsed milliseconds and algorithmic FLOPs (2*M*N*K) of the GEMMs run by `engine`
+ * (GANFFN_GEMM_AUTO = all) since the last collect, and clears the record. */
+void ganffn_gemm_profile_enable(int on);
+int ganffn_gemm_profile_collect(int engine, double* total_ms, double* total_flops, int64_t* launches);
+
 /* ---- primitives (each is also used by the whole-network calls) ------------------------ */
 
 /* y[M,N] = epilogue(x[M,K] @ w[N,K]^T + bias).  Replaces nn.Linear inside

@@ -1,0 +1,232 @@
+"""GPU parity of the whole hot path through the reference-facing module API:
+  * every network, GAN_FFN + MaskedNLLLoss, train_disc / train_gen and Adam against the fixtures the
+    unmodified reference produced (tests/golden, dropout off);
+  * train mode (dropout on) against the CPU oracle with the kernels' own Philox masks injected;
+  * size-independent properties at the full IEMOCAP batch shape (S=94, B=32).
+Tolerance: rtol 1e-4 (north_star), see helpers.RTOL."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    return H.golden()
+
+
+@pytest.fixture(scope="module")
+def nets():
+    ns, ffn = H.build_nets("cuda")
+    for m in list(ns.values()) + [ffn]:
+        m.eval()
+    return ns, ffn
+
+
+@pytest.fixture(scope="module", params=[1, 0], ids=["simt", "auto"])
+def engine(request):
+    from gan_ffn_b200._lib import lib
+    lib().cdll.ganffn_set_gemm_engine(request.param)
+    yield request.param
+    lib().cdll.ganffn_set_gemm_engine(0)
+
+
+def named_grads(module, prefix=""):
+    return {prefix + n: p.grad for n, p in module.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("name", H.NET_ORDER)
+def test_network_matches_reference_fixture(G, nets, engine, name):
+    import gan_ffn_b200 as GB
+    ns, _ = nets
+    m = ns[name]
+    batch = H.golden_batch()
+    m.zero_grad(set_to_none=True)
+    x = H.net_inputs(batch)[name].cuda().requires_grad_(True)
+    y = m(x)
+    if name.endswith("gen"):
+        loss = (y * H.golden_cotangent(batch.seq_len).cuda()).sum()
+    else:
+        loss = GB.BCELoss()(y, torch.ones_like(y))
+    loss.backward()
+    H.assert_close(y.detach().cpu(), G[f"{name}/out"], f"{name} output", atol_frac=1e-5)
+    H.assert_close(loss.item(), G[f"{name}/loss"], f"{name} loss")
+    H.assert_close(x.grad.cpu(), G[f"{name}/dx"], f"{name} dx", atol_frac=H.RTOL)
+    grads = named_grads(m)
+    assert not any(k.startswith("encoder_layer.") for k in grads), "the dead prototype layer must keep grad=None"
+    H.check_grads(grads, G, name)
+
+
+def test_visual_discriminator_on_generated_input_skips_object(G, nets, engine):
+    import gan_ffn_b200 as GB
+    ns, _ = nets
+    m = ns["visual_disc"]
+    m.zero_grad(set_to_none=True)
+    x = H.golden_batch().acoustic.cuda().requires_grad_(True)
+    y = m(x)
+    loss = GB.BCELoss()(y, torch.zeros_like(y))
+    loss.backward()
+    H.assert_close(y.detach().cpu(), G["visual_disc_fake/out"], "prob", atol_frac=1e-5)
+    H.assert_close(loss.item(), G["visual_disc_fake/loss"], "loss")
+    H.assert_close(x.grad.cpu(), G["visual_disc_fake/dx"], "dx", atol_frac=H.RTOL)
+    grads = named_grads(m)
+    # the arena hands every live parameter a gradient view; `object` saw no data so it must be exactly zero
+    assert float(grads.pop("object.weight").abs().max()) == 0.0 and float(grads.pop("object.bias").abs().max()) == 0.0
+    H.check_grads(grads, G, "visual_disc_fake")
+
+
+def test_stage2_step_matches_reference_fixture(G, nets, engine):
+    """train_or_eval_model body (reference train_IEMOCAP.py:151-169)."""
+    import gan_ffn_b200 as GB
+    ns, ffn = nets
+    batch = H.golden_batch().to("cuda")
+    ffn.zero_grad(set_to_none=True)
+    loss_function = GB.MaskedNLLLoss(torch.tensor(H.synthetic.IEMOCAP_LOSS_WEIGHTS).cuda())
+    log_prob, alpha, alpha_f, alpha_b = ffn(batch.acoustic, batch.visual, batch.text)
+    assert (alpha, alpha_f, alpha_b) == ([], [], [])
+    lp_ = log_prob.transpose(0, 1).contiguous().view(-1, log_prob.size()[2])
+    labels_ = batch.label.view(-1)
+    loss = loss_function(lp_, labels_, batch.umask)
+    loss.backward()
+    H.assert_close(log_prob.detach().cpu(), G["ffn/log_prob"], "log_prob", atol_frac=1e-5)
+    H.assert_close(loss.item(), G["ffn/loss"], "loss")
+    grads = named_grads(ffn)
+    assert not any(k.startswith(("lstm.", "smax_fc.")) for k in grads)
+    H.check_grads(grads, G, "ffn")
+
+
+def test_stage1_substeps_and_fused_adam_match_reference_fixture(G, nets, engine):
+    """train_disc / train_gen bodies (reference train_IEMOCAP.py:200-252), dropout off, then one Adam step."""
+    import gan_ffn_b200 as GB
+    ns, _ = nets
+    disc, gen = ns["visual_disc"], ns["acoustic_gen"]
+    batch = H.golden_batch().to("cuda")
+    S = batch.seq_len
+    valid = torch.ones(S, 3, 1, device="cuda")
+    fake = torch.zeros(S, 3, 1, device="cuda")
+    adversarial_loss = GB.BCELoss()
+    saved = {n: p.detach().clone() for n, p in gen.named_parameters()}
+    try:
+        opt_d = GB.FusedAdam(disc, lr=1e-4 / 2, betas=(0.5, 0.6))
+        opt_g = GB.FusedAdam(gen, lr=1e-4, betas=(0.5, 0.6))
+        # train_disc
+        opt_d.zero_grad()
+        real_prob = disc(batch.visual)
+        fusion = gen(batch.acoustic)
+        fake_prob = disc(fusion.detach())
+        d_loss = (adversarial_loss(real_prob, valid) + adversarial_loss(fake_prob, fake)) / 2.0
+        d_loss.backward()
+        H.assert_close(d_loss.item(), G["train_disc/loss"], "d_loss")
+        H.check_grads(named_grads(disc), G, "train_disc")
+        # train_gen
+        opt_g.zero_grad()
+        prob = disc(gen(batch.acoustic))
+        g_loss = adversarial_loss(prob, valid)
+        g_loss.backward()
+        H.assert_close(g_loss.item(), G["train_gen/loss"], "g_loss")
+        ggrads = {k: v.clone() for k, v in named_grads(gen).items()}
+        H.check_grads(ggrads, G, "train_gen")
+        opt_g.step()
+        for i, n in enumerate(str(s) for s in G["adam/names"]):
+            p = dict(gen.named_parameters())[n]
+            delta = (p.detach() - saved[n]).double().cpu().reshape(-1).numpy()[H.probe_index(p.numel())]
+            H.check_adam_delta(delta, G["adam/delta_probe"][i], ggrads[n], 1e-4, n)
+        dead = dict(gen.named_parameters())["encoder_layer.linear1.weight"]
+        assert torch.equal(dead, saved["encoder_layer.linear1.weight"]) and dead.grad is None
+    finally:
+        with torch.no_grad():
+            for n, p in gen.named_parameters():
+                p.copy_(saved[n])
+        gen.zero_grad(set_to_none=True)
+        disc.zero_grad(set_to_none=True)
+
+
+# ---- train mode: the kernels' Philox masks injected into the oracle -----------------------------------------
+def _mask_fn(seed, S, B, nhead, p_head):
+    from gan_ffn_b200.functional import dropout_mask
+
+    def masks(site, shape):
+        if site >= 16 and site < 200 and site % 16 == 0:        # attention probabilities (B,H,S,S)
+            b, h, s, _ = shape
+            return dropout_mask(b * h * s, s, 0.1, seed, site, row_stride=(s + 3) // 4 * 4).cpu().view(shape)
+        p = 0.2 if site == O.SITE_PE else (0.1 if site < 200 else p_head)
+        rows = int(np.prod(shape[:-1]))
+        return dropout_mask(rows, shape[-1], p, seed, site).cpu().view(shape)
+    return masks
+
+
+@pytest.mark.parametrize("name,p_head", [("text_gen", 0.2), ("visual_gen", 0.2), ("acoustic_disc", 0.2), ("visual_disc", 0.2)])
+def test_train_mode_matches_oracle_with_injected_masks(nets, engine, name, p_head):
+    import gan_ffn_b200 as GB
+    from gan_ffn_b200 import functional as GF
+    ns, _ = nets
+    m = ns[name]
+    batch = H.synthetic.make_batch(n_dialogues=2, lengths=[9, 6], seed=77)
+    x_cpu = H.net_inputs(batch)[name]
+    GF.manual_seed(4242)
+    seed = GF.next_seed()
+    GF.manual_seed(4242)
+    m.train()
+    try:
+        m.zero_grad(set_to_none=True)
+        x = x_cpu.cuda().requires_grad_(True)
+        y = m(x)
+        cot = torch.rand(y.shape, generator=torch.Generator().manual_seed(1))
+        (y * cot.cuda()).sum().backward()
+        P = O.params_of(m, dtype=torch.float64, requires_grad=True)
+        xr = x_cpu.double().requires_grad_(True)
+        yr = H.oracle_forward(name, xr, P, _mask_fn(seed, batch.seq_len, 2, H.NHEAD.get(name, 10), p_head))
+        (yr * cot.double()).sum().backward()
+        assert (y.detach().cpu() != H.oracle_forward(name, x_cpu, O.params_of(m)).detach()).any(), "dropout had no effect"
+        H.assert_close(y.detach().cpu(), yr.detach(), f"{name} train-mode output", atol_frac=1e-5)
+        H.assert_close(x.grad.cpu(), xr.grad, f"{name} train-mode dx", atol_frac=H.RTOL)
+        for n, p in m.named_parameters():
+            if p.grad is None:
+                continue
+            H.assert_close(p.grad.cpu(), P[n].grad, f"{name} train-mode grad {n}", atol_frac=H.RTOL)
+    finally:
+        m.eval()
+        m.zero_grad(set_to_none=True)
+
+
+# ---- full-size properties (S=94, B=32: BASELINE config 2) ------------------------------------------------------
+def test_full_size_properties(nets, engine):
+    ns, ffn = nets
+    batch = H.synthetic.make_batch(n_dialogues=32, seq_len=94)
+    cb = batch.to("cuda")
+    with torch.no_grad():
+        lp1 = ffn(cb.acoustic, cb.visual, cb.text)[0]
+        lp2 = ffn(cb.acoustic, cb.visual, cb.text)[0]
+        assert torch.equal(lp1, lp2), "eval forward must be deterministic"
+        assert lp1.shape == (94, 32, 6)
+        # log-probabilities normalise
+        assert torch.allclose(lp1.exp().sum(-1), torch.ones(94, 32, device="cuda"), atol=1e-5)
+        # dialogues are independent: a shard of 4 dialogues (kept at the global pad length) reproduces its slice
+        sub = batch.dialogues([3, 9, 17, 30]).to("cuda")
+        lps = ffn(sub.acoustic, sub.visual, sub.text)[0]
+        H.assert_close(lps.cpu(), lp1[:, [3, 9, 17, 30]].cpu(), "dialogue-shard independence", atol_frac=1e-5)
+        # ... but a dialogue's output does depend on the pad length (no key-padding mask in the reference)
+        short = H.synthetic.make_batch(n_dialogues=2, lengths=[20, 20], seed=5)
+        g = ns["text_gen"]
+        a = g(short.text.cuda())
+        padded = torch.zeros(50, 2, 100)
+        padded[:20] = short.text
+        bpad = g(padded.cuda())[:20]
+        assert (a - bpad).abs().max().item() > 1e-3
+
+
+def test_error_conventions(nets):
+    ns, _ = nets
+    g = ns["text_gen"]
+    with pytest.raises(ValueError, match="110"):
+        g(torch.zeros(111, 1, 100, device="cuda"))          # PositionalEncoding max_len (reference model.py:1179)
+    with pytest.raises(ValueError):
+        g(torch.zeros(10, 1, 512, device="cuda"))           # wrong feature width for a generator
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g(torch.zeros(10, 1, 100))
+    with pytest.raises(ValueError):
+        ns["acoustic_disc"](torch.zeros(10, 1, 512, device="cuda"))   # only the visual discriminator has `object`

@@ -1,0 +1,324 @@
+"""GPU parity of every C-ABI primitive against fp64 CPU restatements (oracle/ganffn_oracle.py).
+
+Tolerance (north_star): rtol 1e-4 in fp32.  Checked as |x - ref| <= 1e-4*|ref| + 1e-5*max|ref|
+(the absolute floor covers entries that cancel to ~0)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [1, 2]  # GANFFN_GEMM_SIMT, GANFFN_GEMM_TC (TC falls back to SIMT tiles for unsupported shapes)
+
+
+@pytest.fixture(scope="module")
+def L():
+    from gan_ffn_b200._lib import lib
+    return lib()
+
+
+@pytest.fixture(autouse=True)
+def _restore_engine(L):
+    yield
+    L.cdll.ganffn_set_gemm_engine(0)
+
+
+def dev(t):
+    return t.to("cuda", torch.float32).contiguous()
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def close(a, e, what, rtol=1e-4, floor=1e-5):
+    H.assert_close(a.detach().double().cpu().numpy(), e.detach().double().cpu().numpy(), what, rtol=rtol, atol_frac=floor)
+
+
+def gemm_ws(L, M, N, K):
+    n = int(L.cdll.ganffn_gemm_scratch_floats(M, N, K))
+    return torch.empty(max(n, 1), device="cuda"), n
+
+
+LINEAR_SHAPES = [(300, 300, 100), (282, 2048, 100), (282, 100, 2048), (50, 1, 16), (37, 6, 100), (3008, 1536, 512),
+                 (3008, 100, 2048), (3008, 2048, 512), (129, 512, 512), (1, 100, 100), (36, 64, 100), (36, 16, 64)]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("M,N,K", LINEAR_SHAPES)
+def test_linear_fwd_plain(L, engine, M, N, K):
+    L.cdll.ganffn_set_gemm_engine(engine)
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, generator=g, dtype=torch.float64)
+    w = torch.randn(N, K, generator=g, dtype=torch.float64) / math.sqrt(K)
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    y = torch.empty(M, N, device="cuda")
+    ws, n = gemm_ws(L, M, N, K)
+    L.call("ganffn_linear_fwd", P(xd), P(wd), P(bd), None, P(y), None, M, N, K, 0, 0, 0.0, 0, 0, P(ws), n, stream())
+    ref = xd.double().cpu() @ wd.double().cpu().T + bd.double().cpu()
+    close(y, ref, f"linear {M}x{N}x{K}", rtol=1e-4, floor=2e-6)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("act,dba", [(1, 0), (2, 1), (3, 1), (0, 0)])
+def test_linear_fwd_epilogues_with_dropout_and_residual(L, engine, act, dba):
+    L.cdll.ganffn_set_gemm_engine(engine)
+    M, N, K = 282, 512, 100
+    g = torch.Generator().manual_seed(11 + act)
+    x, w, b, r = (torch.randn(*s, generator=g) for s in ((M, K), (N, K), (N,), (M, N)))
+    w = w / 10
+    xd, wd, bd, rd = dev(x), dev(w), dev(b), dev(r)
+    y = torch.empty(M, N, device="cuda")
+    pre = torch.empty(M, N, device="cuda")
+    p, seed, site = 0.2, 0xDEADBEEF12345, 201
+    ws, n = gemm_ws(L, M, N, K)
+    L.call("ganffn_linear_fwd", P(xd), P(wd), P(bd), P(rd), P(y), P(pre), M, N, K, act, dba, p, seed, site, P(ws), n,
+           stream())
+    from gan_ffn_b200.functional import dropout_mask
+    mask = dropout_mask(M, N, p, seed, site).double().cpu()
+    v = x.double() @ w.double().T + b.double()
+    f = {0: lambda t: t, 1: torch.relu, 2: O.gelu, 3: torch.sigmoid}[act]
+    if dba:
+        pre_ref = v * mask
+        ref = f(pre_ref) + r.double()
+    else:
+        pre_ref = v
+        ref = f(v) * mask + r.double()
+    close(pre, pre_ref, "pre-activation", floor=2e-6)
+    close(y, ref, "epilogue output", floor=2e-6)
+
+
+def test_dropout_mask_statistics_and_determinism(L):
+    from gan_ffn_b200.functional import dropout_mask
+    for p in (0.1, 0.2, 0.6):
+        m = dropout_mask(4096, 512, p, 1234, 17)
+        keep = (m > 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 3e-3, (p, keep)
+        assert torch.allclose(m[m > 0], torch.tensor(1 / (1 - p), device="cuda"))
+        assert torch.equal(m, dropout_mask(4096, 512, p, 1234, 17))
+        assert not torch.equal(m, dropout_mask(4096, 512, p, 1234, 18))
+        assert not torch.equal(m, dropout_mask(4096, 512, p, 1235, 17))
+    assert torch.equal(dropout_mask(16, 8, 0.0, 1, 1), torch.ones(16, 8, device="cuda"))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("M,N,K", [(282, 2048, 100), (282, 100, 2048), (3008, 512, 2048), (3008, 1536, 512), (50, 1, 16),
+                                   (36, 16, 64)])
+def test_linear_dgrad_and_wgrad(L, engine, M, N, K):
+    L.cdll.ganffn_set_gemm_engine(engine)
+    g = torch.Generator().manual_seed(M + N + K)
+    dy = torch.randn(M, N, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(N)
+    x = torch.randn(M, K, generator=g)
+    r = torch.randn(M, K, generator=g)
+    dyd, wd, xd, rd = dev(dy), dev(w), dev(x), dev(r)
+    dx = torch.empty(M, K, device="cuda")
+    ws, n = gemm_ws(L, M, K, N)
+    L.call("ganffn_linear_dgrad", P(dyd), P(wd), P(rd), P(dx), M, N, K, P(ws), n, stream())
+    close(dx, dy.double() @ w.double() + r.double(), "dgrad", floor=2e-6)
+
+    dw0 = torch.randn(N, K, generator=g)
+    db0 = torch.randn(N, generator=g)
+    for acc in (0, 1):
+        dw, db = dev(dw0).clone(), dev(db0).clone()
+        wsn = int(L.cdll.ganffn_wgrad_scratch_floats(M, N, K))
+        ws2 = torch.empty(max(wsn, 1), device="cuda")
+        L.call("ganffn_linear_wgrad", P(dyd), P(xd), P(dw), P(db), M, N, K, acc, P(ws2), stream())
+        rw = dy.double().T @ x.double() + (dw0.double() if acc else 0)
+        rb = dy.double().sum(0) + (db0.double() if acc else 0)
+        close(dw, rw, f"wgrad acc={acc}", floor=2e-6)
+        close(db, rb, f"bias grad acc={acc}", floor=2e-6)
+
+
+def _attn_ref(qkv, S, B, d, H_, mask=None):
+    hd = d // H_
+    q, k, v = qkv.split(d, dim=-1)
+    f = lambda t: t.reshape(S, B, H_, hd).permute(1, 2, 0, 3)
+    q, k, v = f(q), f(k), f(v)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1)
+    if mask is not None:
+        p = p * mask
+    return (p @ v).permute(2, 0, 1, 3).reshape(S, B, d)
+
+
+@pytest.mark.parametrize("S,B,d,nh,p", [(94, 4, 100, 10, 0.0), (110, 3, 512, 8, 0.0), (5, 2, 32, 4, 0.0), (1, 2, 100, 10, 0.0),
+                                        (37, 3, 100, 10, 0.1), (33, 2, 512, 8, 0.1), (110, 2, 64, 4, 0.1), (7, 3, 64, 2, 0.1)])
+def test_attention_fwd_bwd(L, S, B, d, nh, p):
+    g = torch.Generator().manual_seed(S * 13 + d)
+    qkv = torch.randn(S, B, 3 * d, generator=g).double()
+    do = torch.randn(S, B, d, generator=g).double()
+    qd, dod = dev(qkv), dev(do)
+    o = torch.empty(S, B, d, device="cuda")
+    lse = torch.empty(B * nh * S, device="cuda")
+    dqkv = torch.empty(S, B, 3 * d, device="cuda")
+    seed, site = 987654321, 16
+    L.call("ganffn_attention_fwd", P(qd), P(o), P(lse), S, B, d, nh, p, seed, site, stream())
+    L.call("ganffn_attention_bwd", P(qd), P(o), P(lse), P(dod), P(dqkv), S, B, d, nh, p, seed, site, stream())
+    mask = None
+    if p > 0:
+        from gan_ffn_b200.functional import dropout_mask
+        mask = dropout_mask(B * nh * S, S, p, seed, site, row_stride=(S + 3) // 4 * 4).double().cpu().view(B, nh, S, S)
+    qr = qd.double().cpu().requires_grad_(True)
+    ref = _attn_ref(qr, S, B, d, nh, mask)
+    ref.backward(dod.double().cpu())
+    close(o, ref, "attention out", floor=2e-6)
+    close(dqkv, qr.grad, "attention dqkv", floor=1e-5)
+
+
+@pytest.mark.parametrize("T,d", [(282, 100), (3008, 512), (5, 32), (1, 100)])
+def test_layernorm_fwd_bwd(L, T, d):
+    g = torch.Generator().manual_seed(T + d)
+    z = (torch.randn(T, d, generator=g) * 2 + 0.5).double()
+    gam = torch.randn(d, generator=g).double()
+    bet = torch.randn(d, generator=g).double()
+    dy = torch.randn(T, d, generator=g).double()
+    zd, gd, bd, dyd = dev(z), dev(gam), dev(bet), dev(dy)
+    y = torch.empty(T, d, device="cuda")
+    L.call("ganffn_layernorm_fwd", P(zd), P(gd), P(bd), P(y), T, d, stream())
+    zr = zd.double().cpu().requires_grad_(True)
+    gr = gd.double().cpu().requires_grad_(True)
+    br = bd.double().cpu().requires_grad_(True)
+    ref = O.layer_norm(zr, gr, br)
+    ref.backward(dyd.double().cpu())
+    close(y, ref, "layernorm", floor=2e-6)
+    ws = torch.empty(int(L.cdll.ganffn_layernorm_scratch_floats(T, d)), device="cuda")
+    for acc, p in ((0, 0.0), (1, 0.1)):
+        dz = torch.empty(T, d, device="cuda")
+        dzd = torch.empty(T, d, device="cuda")
+        dg = torch.ones(d, device="cuda")
+        db = torch.ones(d, device="cuda")
+        L.call("ganffn_layernorm_bwd", P(dyd), P(zd), P(gd), P(dz), P(dzd) if p > 0 else None, P(dg), P(db), T, d, acc, p,
+               77, 19, P(ws), stream())
+        close(dz, zr.grad, "ln dz", floor=1e-5)
+        close(dg, gr.grad + acc, "ln dgamma", floor=1e-5)
+        close(db, br.grad + acc, "ln dbeta", floor=1e-5)
+        if p > 0:
+            from gan_ffn_b200.functional import dropout_mask
+            close(dzd, zr.grad * dropout_mask(T, d, p, 77, 19).double().cpu(), "ln dz*mask", floor=1e-5)
+
+
+def test_posenc(L):
+    S, B, d = 94, 5, 100
+    x = torch.rand(S, B, d)
+    pe = O.positional_table(d)
+    y = torch.empty(S, B, d, device="cuda")
+    x_d, pe_d = dev(x), dev(pe)
+    L.call("ganffn_posenc_fwd", P(x_d), P(pe_d), P(y), S, B, d, 0.0, 0, stream())
+    assert torch.equal(y.cpu(), O.positional_encoding(x))          # one fp32 add: bit exact
+    with pytest.raises(ValueError, match="110"):
+        L.call("ganffn_posenc_fwd", P(x_d), P(pe_d), P(y), 111, 1, d, 0.0, 0, stream())
+
+
+def test_fuse_cls_and_masked_nll(L):
+    S, B, dh, C = 23, 5, 100, 6
+    T = S * B
+    g = torch.Generator().manual_seed(5)
+    a, v, t = (torch.randn(T, dh, generator=g) for _ in range(3))
+    w = torch.randn(C, dh, generator=g) / 10
+    b = torch.randn(C, generator=g)
+    target = torch.randint(0, C, (T,), generator=g)
+    mask = (torch.rand(T, generator=g) > 0.3).float()
+    cw = torch.tensor(H.synthetic.IEMOCAP_LOSS_WEIGHTS)
+    fusion = torch.empty(T, dh, device="cuda")
+    logp = torch.empty(T, C, device="cuda")
+    ad, vd, td, wd, bd = dev(a), dev(v), dev(t), dev(w), dev(b)
+    L.call("ganffn_fuse_cls_fwd", P(ad), P(vd), P(td), P(wd), P(bd), P(fusion), P(logp), T, dh, C, stream())
+    ar, vr, tr, wr, br = (z.double().requires_grad_(True) for z in (a, v, t, w, b))
+    lp_ref = torch.log_softmax((ar + vr + tr) @ wr.T + br, -1)
+    close(logp, lp_ref, "log_prob", floor=2e-6)
+    for weight in (cw, None):
+        out = torch.empty(2, device="cuda")
+        tgt, msk = target.cuda(), mask.cuda()
+        wt = None if weight is None else weight.cuda()
+        L.call("ganffn_masked_nll_fwd", P(logp), P(tgt), P(msk), P(wt), P(out), T, C, 0.0, stream())
+        loss_ref = O.masked_nll(lp_ref, target, mask.view(1, -1), None if weight is None else weight.double())
+        close(out[0], loss_ref, "masked nll")
+        dl = torch.ones(1, device="cuda")
+        dpred = torch.empty(T, C, device="cuda")
+        L.call("ganffn_masked_nll_bwd", P(dl), P(out), P(tgt), P(msk), P(wt), P(dpred), T, C, stream())
+        (dlp_ref,) = torch.autograd.grad(loss_ref, lp_ref, retain_graph=True)
+        close(dpred, dlp_ref, "masked nll grad")
+    # backward of fusion+classifier given d_log_prob
+    for z in (ar, vr, tr, wr, br):
+        z.grad = None
+    loss_ref = O.masked_nll(lp_ref, target, mask.view(1, -1), cw.double())
+    loss_ref.backward()
+    dfus = torch.empty(T, dh, device="cuda")
+    dw = torch.empty(C, dh, device="cuda")
+    db = torch.empty(C, device="cuda")
+    ws = torch.empty(int(L.cdll.ganffn_fuse_cls_scratch_floats(T, dh, C)), device="cuda")
+    # dpred currently holds the unweighted gradient; recompute the weighted one
+    out = torch.empty(2, device="cuda")
+    tgt_d, msk_d, cw_d, one_d = target.cuda(), mask.cuda(), cw.cuda(), torch.ones(1, device="cuda")   # keep alive
+    L.call("ganffn_masked_nll_fwd", P(logp), P(tgt_d), P(msk_d), P(cw_d), P(out), T, C, 0.0, stream())
+    L.call("ganffn_masked_nll_bwd", P(one_d), P(out), P(tgt_d), P(msk_d), P(cw_d), P(dpred), T, C, stream())
+    L.call("ganffn_fuse_cls_bwd", P(dpred), P(logp), P(fusion), P(wd), P(dfus), P(dw), P(db), T, dh, C, 0, P(ws), stream())
+    close(dfus, ar.grad, "d_fusion", floor=1e-5)
+    close(dw, wr.grad, "d fc.weight", floor=1e-5)
+    close(db, br.grad, "d fc.bias", floor=1e-5)
+
+
+def test_masked_nll_den_override(L):
+    T, C = 40, 7
+    g = torch.Generator().manual_seed(9)
+    lp = torch.log_softmax(torch.randn(T, C, generator=g), -1)
+    tgt = torch.randint(0, C, (T,), generator=g)
+    msk = torch.ones(T)
+    out = torch.empty(2, device="cuda")
+    lp_d, tgt_d, msk_d = dev(lp), tgt.cuda(), msk.cuda()
+    L.call("ganffn_masked_nll_fwd", P(lp_d), P(tgt_d), P(msk_d), None, P(out), T, C, 80.0, stream())
+    assert abs(out[0].item() - O.masked_nll(lp.double(), tgt, msk.view(1, -1)).item() * 0.5) < 1e-5
+    assert out[1].item() == 80.0
+
+
+def test_bce_fwd_bwd_including_saturation(L):
+    n = 3008
+    g = torch.Generator().manual_seed(3)
+    prob = torch.rand(n, generator=g)
+    prob[:4] = torch.tensor([0.0, 1.0, 1e-30, 1 - 1e-7])      # log clamp at -100 (torch BCELoss)
+    for tval in (1.0, 0.0):
+        tgt = torch.full((n,), tval)
+        out = torch.empty(1, device="cuda")
+        prob_d, tgt_d = dev(prob), dev(tgt)
+        L.call("ganffn_bce_fwd", P(prob_d), P(tgt_d), P(out), n, 1.0, stream())
+        ref = torch.nn.functional.binary_cross_entropy(prob, tgt)
+        assert abs(out.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    pr = torch.rand(n, generator=g) * 0.98 + 0.01
+    prr = pr.double().requires_grad_(True)
+    ref = O.bce(prr, torch.ones(n, dtype=torch.float64))
+    ref.backward()
+    dp = torch.empty(n, device="cuda")
+    half_d, pr_d, ones_d = torch.full((1,), 0.5, device="cuda"), dev(pr), torch.ones(n, device="cuda")
+    L.call("ganffn_bce_bwd", P(half_d), P(pr_d), P(ones_d), P(dp), n, 1.0, stream())
+    close(dp, prr.grad * 0.5, "bce grad")
+
+
+@pytest.mark.parametrize("wd,gs", [(0.0, 1.0), (0.008, 0.5)])
+def test_adam_matches_torch_optim(L, wd, gs):
+    n = 100003   # exercises the n % 4 tail
+    g = torch.Generator().manual_seed(21)
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * 0.01 for _ in range(3)]
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pt], lr=1e-4, betas=(0.5, 0.6), weight_decay=wd)
+    p, m, v = dev(p0), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step, gr in enumerate(grads, 1):
+        pt.grad = gr * gs
+        opt.step()
+        gr_d = dev(gr)
+        L.call("ganffn_adam_step", P(p), P(gr_d), P(m), P(v), n, step, 1e-4, 0.5, 0.6, 1e-8, wd, gs, stream())
+    delta = (p.cpu() - p0).double()
+    ref = (pt.detach() - p0).double()
+    assert (delta - ref).abs().max().item() <= 1e-4 * 3e-4        # three steps of at most lr each
+    with pytest.raises(ValueError):
+        L.call("ganffn_adam_step", P(p), P(p), P(m), P(v), n, 0, 1e-4, 0.5, 0.6, 1e-8, wd, gs, stream())
