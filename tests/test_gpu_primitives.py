@@ -319,6 +319,8 @@ def test_adam_matches_torch_optim(L, wd, gs):
         L.call("ganffn_adam_step", P(p), P(gr_d), P(m), P(v), n, step, 1e-4, 0.5, 0.6, 1e-8, wd, gs, stream())
     delta = (p.cpu() - p0).double()
     ref = (pt.detach() - p0).double()
-    assert (delta - ref).abs().max().item() <= 1e-4 * 3e-4        # three steps of at most lr each
+    # three steps of at most lr each, compared at rtol 1e-4 of the total update plus one fp32 ulp of the parameter
+    tol = 1e-4 * 3e-4 + 2 * torch.finfo(torch.float32).eps * p0.double().abs()
+    assert ((delta - ref).abs() <= tol).all(), float((delta - ref).abs().max())
     with pytest.raises(ValueError):
         L.call("ganffn_adam_step", P(p), P(p), P(m), P(v), n, 0, 1e-4, 0.5, 0.6, 1e-8, wd, gs, stream())
