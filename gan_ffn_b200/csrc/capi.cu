@@ -158,7 +158,7 @@ int ganffn_layernorm_bwd(const float* dy, const float* z, const float* gamma, fl
                          float* dbeta, int T, int d, int accumulate, float p_drop, uint64_t seed, int site,
                          float* scratch, void* stream) {
   GANFFN_CHECK_ARG(dy && z && gamma && dz && dgamma && dbeta, "layernorm_bwd: null pointer");
-  return layernorm_bwd(dy, z, gamma, dz, dz_drop, dgamma, dbeta, T, d, accumulate, p_drop, seed, site, scratch,
+  return layernorm_bwd(dy, z, gamma, dz, dz_drop, dgamma, dbeta, nullptr, T, d, accumulate, p_drop, seed, site, scratch,
                        S(stream));
 }
 

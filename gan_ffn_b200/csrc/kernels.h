@@ -25,8 +25,8 @@ int attention_bwd(const float* qkv, const float* o, const float* lse, const floa
 // rowwise.cu
 int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T, int d, cudaStream_t st);
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
-                  float* dbeta, int T, int d, int accumulate, float p, uint64_t seed, int site, float* scratch,
-                  cudaStream_t st);
+                  float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, uint64_t seed, int site,
+                  float* scratch, cudaStream_t st);
 int64_t layernorm_scratch_floats(int T, int d);
 int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, uint64_t seed, cudaStream_t st);
 enum { EW_GELU_DROP = 0, EW_DGELU_MASK = 1, EW_DSIGMOID_MASK = 2, EW_MASK = 3 };

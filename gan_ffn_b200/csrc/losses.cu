@@ -125,14 +125,23 @@ __global__ void __launch_bounds__(256) fuse_cls_bwd_kernel(const float* __restri
   }
 }
 
-__global__ void fold2_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ out0,
-                             float* __restrict__ out1, int split, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+__global__ void __launch_bounds__(256) fold2_kernel(const float* __restrict__ partial, int nblk, int n, float* out0,
+                                                    float* out1, int split, int accumulate) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + c];
-  float* dst = c < split ? out0 + c : out1 + (c - split);
-  *dst = accumulate ? *dst + s : s;
+  if (c < n)
+    for (int b = ty; b < nblk; b += 8) s += partial[(size_t)b * n + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    float* dst = c < split ? out0 + c : out1 + (c - split);
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 // ---- block reduction helper ------------------------------------------------------------------------------
@@ -272,7 +281,7 @@ int fuse_cls_bwd(const float* dlp, const float* logp, const float* fusion, const
   const size_t smem = ((size_t)C * dh + (size_t)8 * n) * sizeof(float);
   fuse_cls_bwd_kernel<<<grid, 256, smem, st>>>(dlp, logp, fusion, w, d_fusion, scratch, T, dh, C);
   GANFFN_LAUNCHED("fuse_cls_bwd_kernel");
-  fold2_kernel<<<cdiv(n, 256), 256, 0, st>>>(scratch, grid, n, dw, db, C * dh, accumulate);
+  fold2_kernel<<<cdiv(n, 32), 256, 0, st>>>(scratch, grid, n, dw, db, C * dh, accumulate);
   GANFFN_LAUNCHED("fold2_kernel");
   return GANFFN_OK;
 }

@@ -260,8 +260,8 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
 
     // x2 = LN2(z2), z2 = x1 + drop(linear2(h))
     GANFFN_TRY(layernorm_bwd(da, base + sl.z2, P(lo[N2_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N2_W]), G(lo[N2_B]),
-                             T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 3), cx.red, st));
-    GANFFN_TRY(cx.wgrad(dzd, base + sl.h, G(lo[L2_W]), G(lo[L2_B]), T, d, nd.dff, accumulate));
+                             G(lo[L2_B]), T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 3), cx.red, st));
+    GANFFN_TRY(cx.wgrad(dzd, base + sl.h, G(lo[L2_W]), nullptr, T, d, nd.dff, accumulate));
     {
       Epilogue ep; ep.dact = DACT_NONZERO; ep.dact_src = base + sl.h; ep.dact_scale = p_enc > 0.f ? 1.f / (1.f - p_enc) : 1.f;
       GANFFN_TRY(cx.dgrad(dzd, P(lo[L2_W]), scratch + sc.dh, T, d, nd.dff, ep));
@@ -273,8 +273,8 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
     }
     // x1 = LN1(z1), z1 = xin + drop(out_proj(o))
     GANFFN_TRY(layernorm_bwd(db, base + sl.z1, P(lo[N1_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N1_W]), G(lo[N1_B]),
-                             T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 1), cx.red, st));
-    GANFFN_TRY(cx.wgrad(dzd, base + sl.o, G(lo[OUT_W]), G(lo[OUT_B]), T, d, d, accumulate));
+                             G(lo[OUT_B]), T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 1), cx.red, st));
+    GANFFN_TRY(cx.wgrad(dzd, base + sl.o, G(lo[OUT_W]), nullptr, T, d, d, accumulate));
     GANFFN_TRY(cx.dgrad(dzd, P(lo[OUT_W]), scratch + sc.d_o, T, d, d, Epilogue{}));
     GANFFN_TRY(attention_bwd(base + sl.qkv, base + sl.o, base + sl.lse, scratch + sc.d_o, scratch + sc.dqkv, nd.S, nd.B,
                              d, nd.nhead, p_enc, seed, GANFFN_SITE_LAYER(l, 0), st));

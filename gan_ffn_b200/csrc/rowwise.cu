@@ -60,14 +60,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma, float* __restrict__ dz,
                                                             float* __restrict__ dz_drop, float* __restrict__ partial,
                                                             int T, int d, float p_drop, uint64_t seed, uint32_t site) {
-  extern __shared__ __align__(16) float sm[];  // [warps][2][d]
+  extern __shared__ __align__(16) float sm[];  // [warps][3][d]: dgamma, dbeta, colsum(dz after dropout)
   const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = d >> 2;
-  float4 dg[LN_MAXV], db[LN_MAXV], gm[LN_MAXV];
+  float4 dg[LN_MAXV], db[LN_MAXV], gm[LN_MAXV], ds[LN_MAXV];
 #pragma unroll
   for (int k = 0; k < LN_MAXV; ++k) {
     dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int c = lane + 32 * k;
     gm[k] = c < nv ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -124,38 +125,55 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         if (drop) {
           float m[4];
           dropout_scale4(seed, site, (uint64_t)row * d + 4 * c, p_drop, dscale, m);
-          reinterpret_cast<float4*>(dz_drop + (size_t)row * d)[c] = make_float4(r.x * m[0], r.y * m[1], r.z * m[2], r.w * m[3]);
+          r = make_float4(r.x * m[0], r.y * m[1], r.z * m[2], r.w * m[3]);
+          reinterpret_cast<float4*>(dz_drop + (size_t)row * d)[c] = r;
         }
+        ds[k].x += r.x; ds[k].y += r.y; ds[k].z += r.z; ds[k].w += r.w;
       }
     }
   }
   // fold the block's warps
-  float* mine = sm + (size_t)w * 2 * d;
+  float* mine = sm + (size_t)w * 3 * d;
 #pragma unroll
   for (int k = 0; k < LN_MAXV; ++k) {
     const int c = lane + 32 * k;
     if (c < nv) {
       reinterpret_cast<float4*>(mine)[c] = dg[k];
       reinterpret_cast<float4*>(mine + d)[c] = db[k];
+      reinterpret_cast<float4*>(mine + 2 * d)[c] = ds[k];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+  for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
     float s = 0.f;
-    for (int ww = 0; ww < warps; ++ww) s += sm[(size_t)ww * 2 * d + c];
-    partial[(size_t)blockIdx.x * 2 * d + c] = s;
+    for (int ww = 0; ww < warps; ++ww) s += sm[(size_t)ww * 3 * d + c];
+    partial[(size_t)blockIdx.x * 3 * d + c] = s;
   }
 }
 
-// out[c] (+)= sum_b partial[b][c]
-__global__ void fold_partials_kernel(const float* __restrict__ partial, int nblk, int n, float* out0, float* out1,
-                                     int split, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+// out_seg[c % seg] (+)= sum_b partial[b][c] for c in [0, n): 32 columns per block, 8 row lanes, smem fold.
+// Segment s = c / seg goes to out0/out1/out2 (a null segment pointer is skipped).
+__global__ void __launch_bounds__(256) fold_partials_kernel(const float* __restrict__ partial, int nblk, int n, int seg,
+                                                            float* out0, float* out1, float* out2, int accumulate) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + c];
-  float* dst = c < split ? out0 + c : out1 + (c - split);
-  *dst = accumulate ? *dst + s : s;
+  if (c < n)
+    for (int b = ty; b < nblk; b += 8) s += partial[(size_t)b * n + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    const int sidx = c / seg;
+    float* base = sidx == 0 ? out0 : sidx == 1 ? out1 : out2;
+    if (base) {
+      float* dst = base + (c - sidx * seg);
+      *dst = accumulate ? *dst + t : t;
+    }
+  }
 }
 
 // ---- positional encoding ------------------------------------------------------------------------------
@@ -255,18 +273,20 @@ int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* 
 
 static int ln_bwd_blocks(int T) { return min(cdiv(T, 8), 148 * 2); }
 
-int64_t layernorm_scratch_floats(int T, int d) { return (int64_t)ln_bwd_blocks(T) * 2 * d; }
+int64_t layernorm_scratch_floats(int T, int d) { return (int64_t)ln_bwd_blocks(T) * 3 * d; }
 
+// dbias_sub (optional): column sums of the gradient that flows into the sublayer branch (dz after its
+// dropout mask) = the bias gradient of the linear layer that fed this LayerNorm's residual add.
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
-                  float* dbeta, int T, int d, int accumulate, float p, uint64_t seed, int site, float* scratch,
-                  cudaStream_t st) {
+                  float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, uint64_t seed, int site,
+                  float* scratch, cudaStream_t st) {
   GANFFN_CHECK_ARG(T > 0 && d > 0 && d % 4 == 0 && d <= 512, "layernorm: d=%d must be a multiple of 4 and <= 512", d);
   GANFFN_CHECK_ARG(scratch != nullptr, "layernorm_bwd: scratch is null");
   const int grid = ln_bwd_blocks(T);
-  layernorm_bwd_kernel<<<grid, 256, (size_t)8 * 2 * d * sizeof(float), st>>>(dy, z, gamma, dz, dz_drop, scratch, T, d, p,
+  layernorm_bwd_kernel<<<grid, 256, (size_t)8 * 3 * d * sizeof(float), st>>>(dy, z, gamma, dz, dz_drop, scratch, T, d, p,
                                                                              seed, (uint32_t)site);
   GANFFN_LAUNCHED("layernorm_bwd_kernel");
-  fold_partials_kernel<<<cdiv(2 * d, 256), 256, 0, st>>>(scratch, grid, 2 * d, dgamma, dbeta, d, accumulate);
+  fold_partials_kernel<<<cdiv(3 * d, 32), 256, 0, st>>>(scratch, grid, 3 * d, d, dgamma, dbeta, dbias_sub, accumulate);
   GANFFN_LAUNCHED("fold_partials_kernel");
   return GANFFN_OK;
 }
@@ -307,7 +327,7 @@ int colsum(const float* a, int M, int N, float* out, int accumulate, float* scra
   dim3 grid(cdiv(N, 32), yb);
   colsum_kernel<<<grid, 256, 0, st>>>(a, M, N, rpb, scratch);
   GANFFN_LAUNCHED("colsum_kernel");
-  fold_partials_kernel<<<cdiv(N, 256), 256, 0, st>>>(scratch, yb, N, out, out, N, accumulate);
+  fold_partials_kernel<<<cdiv(N, 32), 256, 0, st>>>(scratch, yb, N, N, out, nullptr, nullptr, accumulate);
   GANFFN_LAUNCHED("fold_partials_kernel");
   return GANFFN_OK;
 }
