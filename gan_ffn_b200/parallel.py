@@ -55,6 +55,12 @@ class GradReducer:
         for w in works:
             w.wait()
 
+    def global_sum(self, value: float, device) -> float:
+        """Sum of a host scalar over the group (e.g. dialogues per rank -> global batch size)."""
+        t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
     def global_nll_denominator(self, label: torch.Tensor, umask: torch.Tensor, weight: Optional[torch.Tensor]) -> float:
         """sum over the *global* batch of w[label]*umask (MaskedNLLLoss denominator, model.py:78-80)."""
         m = umask.reshape(-1).to(torch.float32)

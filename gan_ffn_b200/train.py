@@ -71,7 +71,8 @@ class GANTrainer:
         self.opt_text_G = mk(text_gen, lr * 1.1)
         self.opt_text_D = mk(text_disc, lr / 2)
         self.adversarial_loss = M.BCELoss()
-        self.adversarial_loss.scale = 1.0 / world_size   # mean over the *global* S*B under dialogue sharding
+        self.grad_reducer, self.world_size = grad_reducer, world_size
+        self._bce_scale = {}
 
     def batch(self, data: Batch) -> Dict[str, torch.Tensor]:
         """The twelve sub-steps of one batch, in the reference's order (train_IEMOCAP.py:355-382).
@@ -83,6 +84,12 @@ class GANTrainer:
         valid = torch.ones(seq_len, batch_size, 1, device=real_text.device)
         fake = torch.zeros(seq_len, batch_size, 1, device=real_text.device)
         adv = self.adversarial_loss
+        # BCELoss is a mean over the *global* S*B slots: each rank contributes local_mean * (B_local / B_global)
+        # (= 1/world_size for equal shards), so the summed shard gradients equal the single-device gradient.
+        if self.grad_reducer is not None:
+            if batch_size not in self._bce_scale:
+                self._bce_scale[batch_size] = batch_size / self.grad_reducer.global_sum(batch_size, real_text.device)
+            adv.scale = self._bce_scale[batch_size]
         loss = {}
         loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["acoustic_gen"], real_acoustic, self.opt_visual_D, adv, valid, fake)
         loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["visual_disc"], self.opt_acoustic_G, adv, valid, fake)

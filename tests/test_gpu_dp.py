@@ -1,0 +1,81 @@
+"""GPU, >= 2 devices, NCCL: dialogue-sharded training step through the CUDA path equals the single-GPU step on
+the whole global batch (gradients after the all-reduce; losses).  Skipped on a 1-GPU box."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import gan_ffn_b200 as GB
+    from gan_ffn_b200 import parallel, synthetic, train
+    parallel.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    red = parallel.GradReducer()
+    w = torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev)
+    glob = synthetic.make_batch(n_dialogues=6, lengths=[40, 17, 33, 8, 25, 40], seed=9)
+
+    def run(batch, reducer):
+        nets, ffn = train.build_networks(device=dev)
+        for m in list(nets.values()) + [ffn]:
+            m.eval()                                           # dropout off: the comparison must be deterministic
+        b = batch.to(dev)
+        # stage 2
+        lossf = GB.MaskedNLLLoss(w)
+        if reducer is not None:
+            lossf.den_override = reducer.global_nll_denominator(b.label, b.umask, w)
+        ffn.zero_grad(set_to_none=True)
+        lp = ffn(b.acoustic, b.visual, b.text)[0]
+        loss2 = lossf(lp.transpose(0, 1).contiguous().view(-1, 6), b.label.view(-1), b.umask)
+        loss2.backward()
+        # stage 1, one discriminator pass
+        bce = GB.BCELoss()
+        if reducer is not None:
+            bce.scale = b.n_dialogues / reducer.global_sum(b.n_dialogues, dev)
+        d = nets["visual_disc"]
+        d.zero_grad(set_to_none=True)
+        prob = d(b.visual)
+        loss1 = bce(prob, torch.ones_like(prob))
+        loss1.backward()
+        bufs = [m.arena().grad for m in (nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], d)]
+        bufs += [ffn.fc.weight.grad, ffn.fc.bias.grad]
+        losses = torch.stack([loss2.detach(), loss1.detach()])
+        if reducer is not None:
+            reducer.reduce(bufs)
+            dist.all_reduce(losses)
+        return [t.clone() for t in bufs], losses
+
+    g_dp, l_dp = run(parallel.shard_batch(glob, world, rank), red)
+    g_one, l_one = run(glob, None)
+    ok = {"loss": bool(torch.allclose(l_dp, l_one, rtol=1e-4, atol=0))}
+    for i, (a, e) in enumerate(zip(g_dp, g_one)):
+        ok[f"grad{i}"] = float((a - e).abs().max()) <= 1e-4 * float(e.abs().max()) + 1e-12
+    if rank == 0:
+        torch.save(ok, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_dp_step_equals_single_gpu_step(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ok.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    ok = torch.load(out)
+    assert all(ok.values()), ok
