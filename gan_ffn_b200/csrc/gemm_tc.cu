@@ -1,41 +1,62 @@
 // tcgen05 GEMM engine with fp32 parity: 3xTF32 error-compensated products on the 5th-gen tensor
 // cores (kind::tf32), fp32 accumulators in TMEM.
 //
-//   C[M,N] = op(A)[M,K] * op(B)[K,N]   (fp32 in, fp32 out, shared fused epilogue)
+//   C[M,N] = op(A)[M,K] * op(B)[K,N]   (fp32 in, fp32 out, fused epilogue)
 //
 // Why 3xTF32: north_star asks for rtol 1e-4 against the fp32 reference through 8 post-norm layers and
 // their backward; one TF32 pass (10-bit mantissa) cannot hold that.  Each operand x is split as
 // x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); the product uses hi*hi + lo*hi + hi*lo
 // (the dropped lo*lo term and the rounding of lo are ~2^-21 relative), three MMAs per K-step.
 //
-// Structure of one CTA (one 128 x BN output tile, optional split-K slice):
-//   warps 0-7  producers: coalesced 128-bit global loads of the fp32 A/B tiles (double-buffered in
-//              registers), hi/lo split, conflict-free st.shared into the canonical SWIZZLE_128B UMMA
-//              layouts (K-major or MN-major, so nn.Linear forward, dgrad and wgrad all read their
-//              operands as they lie in HBM, no transposed copies), fence.proxy.async, mbarrier arrive.
-//              Afterwards the same warps run the epilogue: tcgen05.ld (TMEM -> registers), a per-warp
-//              smem transpose so global traffic is row-contiguous, fused epilogue, 128-bit stores.
-//   warp 8     one elected thread issues tcgen05.mma (12 per 32-wide K block) and tcgen05.commit to
-//              release smem stages / publish the accumulator; it also owns the TMEM allocation.
-// TMA is deliberately not used for the operands: they must pass through registers anyway for the
-// hi/lo split, and the producer warps have the time (3 MMAs per loaded byte).
+// Data flow of one CTA (one 128 x 128 output tile, optional split-K slice), 17 warps:
+//   warps 0-7   A producers.  Thread = one row of the tile (TMEM lane), half of a 32-wide K block.
+//               global -> registers (ring of 3 K blocks in flight) -> hi/lo split -> tcgen05.st into the
+//               TMEM A ring.  The A operand is read by the tensor core from TMEM (".ts" form of
+//               tcgen05.mma): an SS-form 128x128x8 tf32 MMA needs 8 KB of shared-memory reads per 64
+//               cycles, i.e. the whole 128 B/clk shared-memory port, leaving nothing for the producers'
+//               writes (r1 in-kernel timeline: 2200 cycles per K block against 768 of MMA).  With A in
+//               TMEM the port carries only B: 64 B/clk of MMA reads + 42 B/clk of producer writes.
+//   warps 8-15  B producers.  global -> registers (ring of 3) -> hi/lo split -> conflict-free st.shared
+//               into the canonical UMMA layouts (K-major SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B), so
+//               forward (X W^T), dgrad (dY W) and wgrad (dY^T X) read W / X as they lie in HBM.
+//   warp 16     one elected thread issues tcgen05.mma (3 per 8-wide K step) and tcgen05.commit; owns TMEM.
+//   epilogue    all 16 producer warps: one 32x32 sub-tile each (TMEM -> registers -> smem transpose ->
+//               row-contiguous 128-bit global traffic) with a mode-specialised fused epilogue.
+// One full/empty mbarrier pair per stage covers both operand rings (arrivals are per warp, not per
+// thread: 512 arrivals on one mbarrier word serialise for ~1000 cycles per K block).
 #include "kernels.h"
 
 namespace ganffn {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;               // fp32 elements per K block = one 128-byte swizzle row
-constexpr int NPROD = 256;           // producer / epilogue threads
-constexpr int NTHREADS = NPROD + 32; // + MMA warp
-constexpr int A_TILE = BM * BK * 4;  // bytes of one A tile (hi or lo)
+constexpr int BN = 128;
+constexpr int BK = 32;                  // fp32 elements per K block = one 128-byte swizzle row
+constexpr int NAW = 8, NBW = 8;         // A / B producer warps
+constexpr int NPW = NAW + NBW;
+constexpr int NB = NBW * 32;            // B producer threads
+constexpr int NTHREADS = (NPW + 1) * 32;
+constexpr int STAGES = 4;
+constexpr int RING = 3;                 // K blocks each producer thread keeps in flight in registers
+constexpr int B_TILE = BN * BK * 4;     // bytes of one B tile (hi or lo)
+constexpr int STAGE = 2 * B_TILE;
+constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TM_MAIN = 0, TM_CORR = BN, TM_A = 2 * BN;   // TMEM columns; A ring: 64 per stage (32 hi | 32 lo)
+constexpr int TM_COLS = 512;
+static_assert(TM_A + STAGES * 64 <= TM_COLS, "TMEM budget");
+static_assert(NPW * 32 * 36 * 4 <= STAGES * STAGE, "epilogue staging reuses the B ring");
 
-template <int BN> struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int B_TILE = BN * BK * 4;
-  static constexpr int STAGE = 2 * (A_TILE + B_TILE);
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+enum { EPI_PLAIN = 0, EPI_DROP = 1, EPI_FULL = 2 };
+
+#ifdef GANFFN_TC_TRACE
+__device__ long long g_tc_trace[128];
+#define TR(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_trace[i] = clock64(); } while (0)
+__device__ int g_tc_dbg = 0;
+#define DBG(bit) (g_tc_dbg & (bit))
+#else
+#define DBG(bit) 0
+#define TR(i) do {} while (0)
+#endif
 
 struct TcParams {
   const float* A; int lda;
@@ -127,131 +148,367 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// ---- operand tile movers ----------------------------------------------------------------------------------
-// One tile = R rows (M or N extent) x 32 k.  CH = 16-byte chunks per producer thread.
-template <int R> struct Mover {
-  static constexpr int CH = R * 8 / NPROD;
 
-  // global -> registers.  KMAJ: element (r,k) at base[(row0+r)*ld + k]; else at base[k*ld + row0 + r].
-  template <bool KMAJ>
-  static __device__ __forceinline__ void load(float4 (&v)[CH], const float* __restrict__ base, int ld, int row0,
-                                              int rows, int k0, int kend, int t) {
+// A operand from tensor memory (".ts"): lanes = rows of the tile, one tf32 per 32-bit column.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- A operand: registers -> TMEM -----------------------------------------------------------------------------
+// One thread = one row (TMEM lane) and 16 consecutive k of the K block (64 bytes of a K-major row).
+// K-major A is loaded quad-cooperatively: in load i the four lanes of a quad read the 64 contiguous bytes of row
+// 4*(lane/4)+i, so one warp instruction touches 8 rows x 2 full sectors instead of 32 rows x half a sector
+// (ncu r1: the thread-per-row pattern made the LSU/L1 miss path the limiter at ~17 B/clk/SM); a 4x4 butterfly
+// of shuffles hands every lane its own row afterwards.
+template <bool KMAJ>
+__device__ __forceinline__ void load_a(float (&v)[16], const float* __restrict__ A, int lda, int row_base, int lane,
+                                       int M, int k0, int kend) {
+  if (KMAJ) {   // A stored [M, lda], k contiguous
+    const int g4 = lane & ~3, a = lane & 3;
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const int q = t + i * NPROD;
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (KMAJ) {
-        const int r = q >> 3, c = q & 7;
-        const int gr = row0 + r, gk = k0 + c * 4;
-        if (gr < rows && gk < kend) v[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gr * ld + gk));
-      } else {
-        const int k = q / (R / 4), mq = q % (R / 4);
-        const int gk = k0 + k, gr = row0 + mq * 4;
-        if (gk < kend && gr < rows) v[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gk * ld + gr));
+    for (int i = 0; i < 4; ++i) {
+      const int grow = row_base + g4 + i;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < M && k0 + 4 * a < kend) x = __ldg(reinterpret_cast<const float4*>(A + (size_t)grow * lda + k0 + 4 * a));
+      v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    }
+  } else {      // A stored [K, lda], m contiguous: the warp reads 128 contiguous bytes per k
+    const int grow = row_base + lane;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = 0.f;
+      if (grow < M && k0 + j < kend) v[j] = __ldg(A + (size_t)(k0 + j) * lda + grow);
+    }
+  }
+}
+
+// v[4*i + c]: chunk (lane%4) of row 4*(lane/4)+i  ->  chunk i of the lane's own row (4x4 transpose inside the quad).
+__device__ __forceinline__ void quad_transpose(float (&v)[16], int lane) {
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const bool up = (lane >> b) & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((i >> b) & 1) continue;
+      const int i2 = i | (1 << b);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float send = up ? v[4 * i + c] : v[4 * i2 + c];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1 << b);
+        if (up) v[4 * i + c] = recv; else v[4 * i2 + c] = recv;
       }
     }
   }
+}
 
-  // registers -> hi/lo split -> swizzled smem tiles
-  template <bool KMAJ>
-  static __device__ __forceinline__ void store(const float4 (&v)[CH], uint8_t* hi, uint8_t* lo, int t) {
+template <bool KMAJ>
+__device__ __forceinline__ void store_a(float (&v)[16], uint32_t taddr_hi, int lane) {
+  if (KMAJ && !DBG(4)) quad_transpose(v, lane);
+  uint32_t h[16], l[16];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const int q = t + i * NPROD;
-      uint32_t off;
-      if (KMAJ) {
-        const int r = q >> 3, c = q & 7;
-        off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-      } else {
-        const int k = q / (R / 4), mq = q % (R / 4);
-        // 512-byte atoms ordered [k-group of 4][m-group of 32]: LBO = 512 B, SBO = (R/32) * 512 B
-        off = (uint32_t)(((k >> 2) * (R / 32) + (mq >> 3)) * 512 + (k & 3) * 128 + ((((mq & 7) >> 1) ^ (k & 3)) << 5) +
-                         ((mq & 1) << 4));
-      }
-      const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      uint32_t h[4], l[4];
+  for (int j = 0; j < 16; ++j) {
+    h[j] = tf32_rna(v[j]);
+    l[j] = tf32_rna(v[j] - __uint_as_float(h[j]));
+  }
+  tmem_st16(taddr_hi, h);
+  tmem_st16(taddr_hi + 32, l);
+  tmem_st_wait();
+}
+
+// ---- B operand: registers -> swizzled shared memory --------------------------------------------------------------
+// One tile = BN rows (N extent) x 32 k, 4 16-byte chunks per B-producer thread.
+constexpr int BCH = BN * 8 / NB;
+
+// KMAJ: element (n,k) at base[(row0+n)*ld + k]; else at base[k*ld + row0 + n].
+template <bool KMAJ>
+__device__ __forceinline__ void load_b(float4 (&v)[BCH], const float* __restrict__ base, int ld, int row0, int rows,
+                                       int k0, int kend, int tb) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        h[j] = tf32_rna(x[j]);
-        l[j] = tf32_rna(x[j] - __uint_as_float(h[j]));
-      }
-      *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  for (int i = 0; i < BCH; ++i) {
+    const int q = tb + i * NB;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KMAJ) {
+      const int r = q >> 3, c = q & 7;
+      const int gr = row0 + r, gk = k0 + c * 4;
+      if (gr < rows && gk < kend) v[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gr * ld + gk));
+    } else {
+      const int k = q / (BN / 4), mq = q % (BN / 4);
+      const int gk = k0 + k, gr = row0 + mq * 4;
+      if (gk < kend && gr < rows) v[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gk * ld + gr));
     }
   }
-};
+}
+
+template <bool KMAJ>
+__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint8_t* hi, uint8_t* lo, int tb) {
+#pragma unroll
+  for (int i = 0; i < BCH; ++i) {
+    const int q = tb + i * NB;
+    uint32_t off;
+    if (KMAJ) {
+      const int r = q >> 3, c = q & 7;
+      off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    } else {
+      const int k = q / (BN / 4), mq = q % (BN / 4);
+      // 512-byte atoms ordered [k-group of 4][n-group of 32]: LBO = 512 B, SBO = (BN/32) * 512 B
+      off = (uint32_t)(((k >> 2) * (BN / 32) + (mq >> 3)) * 512 + (k & 3) * 128 + ((((mq & 7) >> 1) ^ (k & 3)) << 5) +
+                       ((mq & 1) << 4));
+    }
+    const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = tf32_rna(x[j]);
+      l[j] = tf32_rna(x[j] - __uint_as_float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---- epilogue of one 32 x 32 sub-tile (already transposed into `stage`, 32 rows x 36 floats) ------------------------
+// Lane -> rows i8*4 + lane/8 (i8 = 0..7), columns (lane%8)*4 .. +3: every global access is a 128-byte row segment.
+template <int EPI>
+__device__ __forceinline__ void epilogue_subtile(const TcParams& p, const float* stage, int m_base, int n_base, int lane,
+                                                 bool split, int z) {
+  const int cq = (lane & 7) * 4, r0 = lane >> 3;
+  const int n = n_base + cq;
+  if (split) {
+    if (n < p.Np) {
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int rr = i8 * 4 + r0, m = m_base + rr;
+        if (m < p.M)
+          *reinterpret_cast<float4*>(p.partial + ((size_t)z * p.M + m) * p.Np + n) =
+              *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+      }
+    }
+    return;
+  }
+  if (EPI == EPI_FULL) {
+#pragma unroll 1
+    for (int i8 = 0; i8 < 8; ++i8) {
+      const int rr = i8 * 4 + r0;
+      const float4 v4 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+      float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      epilogue_store4(p.ep, p.C, p.ldc, p.M, p.N, m_base + rr, n, v);
+    }
+    return;
+  }
+  // Vector fast paths (host guarantees N % 4 == 0 and 16-byte alignment of every row segment touched).
+  if (n >= p.N) return;
+  const Epilogue& ep = p.ep;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+  const float* aux_base = ep.residual ? ep.residual : (EPI == EPI_DROP && ep.dact == DACT_NONZERO ? ep.dact_src : nullptr);
+  const int aux_ld = ep.residual ? ep.ldr : p.ldc;
+  float4 aux[8], old[8];
+#pragma unroll
+  for (int i8 = 0; i8 < 8; ++i8) {
+    const int m = m_base + i8 * 4 + r0;
+    aux[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+    old[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < p.M) {
+      if (aux_base) aux[i8] = *reinterpret_cast<const float4*>(aux_base + (size_t)m * aux_ld + n);
+      if (ep.beta != 0.0f) old[i8] = *reinterpret_cast<const float4*>(p.C + (size_t)m * p.ldc + n);
+    }
+  }
+  const bool relu = EPI == EPI_DROP && ep.act == GANFFN_ACT_RELU;
+  const bool drop = EPI == EPI_DROP && ep.p_drop > 0.0f && ep.dact == DACT_NONE;
+  const bool dnz = EPI == EPI_DROP && ep.dact == DACT_NONZERO;
+  const float dscale = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
+#pragma unroll
+  for (int i8 = 0; i8 < 8; ++i8) {
+    const int rr = i8 * 4 + r0, m = m_base + rr;
+    if (m >= p.M) continue;
+    const float4 a4 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+    float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+    const float ax[4] = {aux[i8].x, aux[i8].y, aux[i8].z, aux[i8].w};
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.0f;
+    }
+    if (drop) {
+      float msk[4];
+      dropout_scale4(ep.seed, ep.site, (uint64_t)m * (uint64_t)p.N + (uint64_t)n, ep.p_drop, dscale, msk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= msk[j];
+    }
+    if (dnz) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ax[j] != 0.0f ? v[j] * ep.dact_scale : 0.0f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += ax[j];   // residual (zeros when absent)
+    }
+    if (ep.beta != 0.0f) {
+      v[0] += ep.beta * old[i8].x; v[1] += ep.beta * old[i8].y; v[2] += ep.beta * old[i8].z; v[3] += ep.beta * old[i8].w;
+    }
+    *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
-template <int BN, bool TA, bool TB>
+template <bool TA, bool TB, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) {
-  using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
-  // bars[0..S) full, [S..2S) empty, [2S] accum; then the TMEM base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* full = bars;                 // [STAGES] producers (one arrival per warp) -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES] MMA (tcgen05.commit) -> producers
+  uint64_t* accum = bars + 2 * STAGES;   // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
+  if (t == 0) TR(0);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * p.k_per_split;
   const int kend = min(p.K, kbeg + p.k_per_split);
   const int nkb = (kend - kbeg + BK - 1) / BK;
 
   if (t == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(bars + s), NPROD);
-      mbar_init(smem_u32(bars + C::STAGES + s), 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full + s), NPW);
+      mbar_init(smem_u32(empty + s), 1);
     }
-    mbar_init(smem_u32(bars + 2 * C::STAGES), 1);
+    mbar_init(smem_u32(accum), 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 2 * BN);   // main + correction accumulators
+  if (warp == NPW) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (t == 0) TR(1);
 
-  if (warp < 8) {
-    // ================= producers =================
-    using MA = Mover<BM>;
-    using MB = Mover<BN>;
-    float4 a0[MA::CH], b0[MB::CH], a1[MA::CH], b1[MB::CH];
-    auto gload = [&](float4 (&ra)[MA::CH], float4 (&rb)[MB::CH], int kb) {
-      const int k0 = kbeg + kb * BK;
-      MA::template load<!TA>(ra, p.A, p.lda, m0, p.M, k0, kend, t);
-      MB::template load<TB>(rb, p.B, p.ldb, n0, p.N, k0, kend, t);
-    };
-    auto consume = [&](const float4 (&ra)[MA::CH], const float4 (&rb)[MB::CH], int kb) {
-      const int s = kb % C::STAGES;
-      const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
-      mbar_wait(smem_u32(bars + C::STAGES + s), ph ^ 1u);
-      uint8_t* st = smem + s * C::STAGE;
-      MA::template store<!TA>(ra, st, st + A_TILE, t);
-      MB::template store<TB>(rb, st + 2 * A_TILE, st + 2 * A_TILE + C::B_TILE, t);
-      fence_proxy_async();
-      mbar_arrive(smem_u32(bars + s));
-    };
-    if (nkb > 0) gload(a0, b0, 0);
-    for (int kb = 0; kb < nkb; kb += 2) {
-      if (kb + 1 < nkb) gload(a1, b1, kb + 1);
-      consume(a0, b0, kb);
-      if (kb + 2 < nkb) gload(a0, b0, kb + 2);
-      if (kb + 1 < nkb) consume(a1, b1, kb + 1);
-    }
-
-    // ================= epilogue =================
-    mbar_wait(smem_u32(bars + 2 * C::STAGES), 0);
-    tc_fence_after();
-    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);   // private 32 x 36 fp32 transpose buffer
+  if (warp < NAW) {
+    // ================= A producers: global -> registers -> TMEM =================
     const int quad = warp & 3, half = warp >> 2;
-    const bool split = gridDim.z > 1;
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 2; cc += 32) {
-      const int col0 = half * (BN / 2) + cc;
+    const int row_base = m0 + quad * 32;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TM_A + half * 16);
+    float buf[RING][16];
+#pragma unroll
+    for (int r = 0; r < RING; ++r)
+      if (r < nkb) load_a<!TA>(buf[r], p.A, p.lda, row_base, lane, p.M, kbeg + r * BK + half * 16, kend);
+    for (int kb0 = 0; kb0 < nkb; kb0 += RING) {
+#pragma unroll
+      for (int r = 0; r < RING; ++r) {
+        const int kb = kb0 + r;
+        if (kb < nkb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+          mbar_wait(smem_u32(empty + s), ph ^ 1u);
+          tc_fence_after();
+          if (!DBG(1)) store_a<!TA>(buf[r], trow + (uint32_t)(s * 64), lane);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(full + s));
+          if (kb + RING < nkb) load_a<!TA>(buf[r], p.A, p.lda, row_base, lane, p.M, kbeg + (kb + RING) * BK + half * 16, kend);
+          if (t == 0 && kb < 16) TR(8 + kb);
+        }
+      }
+    }
+  } else if (warp < NPW) {
+    // ================= B producers: global -> registers -> shared memory =================
+    const int tb = t - NAW * 32;
+    float4 buf[RING][BCH];
+#pragma unroll
+    for (int r = 0; r < RING; ++r)
+      if (r < nkb) load_b<TB>(buf[r], p.B, p.ldb, n0, p.N, kbeg + r * BK, kend, tb);
+    for (int kb0 = 0; kb0 < nkb; kb0 += RING) {
+#pragma unroll
+      for (int r = 0; r < RING; ++r) {
+        const int kb = kb0 + r;
+        if (kb < nkb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+          mbar_wait(smem_u32(empty + s), ph ^ 1u);
+          uint8_t* st = smem + s * STAGE;
+          if (!DBG(2)) store_b<TB>(buf[r], st, st + B_TILE, tb);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(full + s));
+          if (kb + RING < nkb) load_b<TB>(buf[r], p.B, p.ldb, n0, p.N, kbeg + (kb + RING) * BK, kend, tb);
+          if (tb == 0 && kb < 16) TR(24 + kb);
+        }
+      }
+    }
+  } else {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const int n_mma = min(BN, (int)((p.N - n0 + 15) & ~15));   // UMMA N: multiple of 16
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TB ? 0u : 1u) << 16) | ((uint32_t)(n_mma >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      // Descriptors are built once; per MMA only the 14-bit start-address field (low word) moves.  The issue
+      // loop must stay a handful of instructions per MMA: this warp shares its scheduler with four busy
+      // producer warps (r1 timeline: 1600 cycles per K block with the descriptors rebuilt inside the loop).
+      const uint32_t b_lbo = TB ? 16 : 512, b_sbo = TB ? 1024 : (BN / 32) * 512, b_lt = TB ? 2u : 1u;
+      const uint64_t bdesc0 = make_desc(smem_u32(smem), b_lbo, b_sbo, b_lt);
+      const uint32_t bdesc_hi32 = (uint32_t)(bdesc0 >> 32), bdesc_lo32 = (uint32_t)bdesc0;
+      // B: K-major -> advance 32 B inside the swizzle row; MN-major -> advance two 4-k atom groups
+      constexpr uint32_t B_JSTEP = (TB ? 32u : 2u * (BN / 32) * 512u) >> 4;
+      const uint32_t d_main = tmem_base + TM_MAIN, d_corr = tmem_base + TM_CORR;
+      // The tensor core accumulates in fp32 with truncation, so every accumulation step costs up to one ulp of
+      // the running sum.  The two correction products (2^-11 of the result) go to their own accumulator: the
+      // main one then sees K/8 accumulations instead of 3K/8, and the corrections' own truncation error is
+      // scaled down by 2^-11.  The epilogue adds the two in round-to-nearest.
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(smem_u32(full + s), ph);
+        tc_fence_after();
+        if (kb < 16) TR(48 + 2 * kb);
+        const uint32_t b_lo32 = bdesc_lo32 + (uint32_t)((s * STAGE) >> 4);
+        const uint32_t a_hi = tmem_base + (uint32_t)(TM_A + s * 64);
+        const int ksteps = min(BK / 8, (kend - (kbeg + kb * BK) + 7) >> 3);   // skip all-zero K steps of a ragged tail
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          if (j < ksteps) {
+            const uint64_t dbh = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP);
+            const uint64_t dbl = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP + (B_TILE >> 4));
+            const uint32_t acc = (j > 0 || kb > 0) ? 1u : 0u;
+            umma_tf32_ts(d_corr, a_hi + 32 + 8 * j, dbh, idesc, acc);
+            umma_tf32_ts(d_corr, a_hi + 8 * j, dbl, idesc, 1u);
+            umma_tf32_ts(d_main, a_hi + 8 * j, dbh, idesc, acc);
+          }
+        }
+        umma_commit(smem_u32(empty + s));   // frees the stage (both rings) when these MMAs retire
+        if (kb < 16) TR(49 + 2 * kb);
+      }
+      umma_commit(smem_u32(accum));         // accumulators complete
+    }
+    __syncwarp();
+  }
+
+  if (warp < NPW) {
+    // ================= epilogue: warp -> TMEM lane quadrant warp%4, columns 32*(warp/4) .. +31 =================
+    if (t == 0) TR(3);
+    mbar_wait(smem_u32(accum), 0);
+    tc_fence_after();
+    if (t == 0) TR(4);
+    const int quad = warp & 3, col0 = (warp >> 2) * 32;
+    if (nkb > 0 && n0 + col0 < p.N) {
+      float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);   // private 32 x 36 fp32 transpose buffer
       uint32_t r[32], rl[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, r);
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + col0), rl);
+      const uint32_t tr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
+      tmem_ld32(tr + TM_MAIN, r);
+      tmem_ld32(tr + TM_CORR, rl);
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -263,64 +520,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
         *reinterpret_cast<float4*>(stage + lane * 36 + q * 4) = o;
       }
       __syncwarp();
-      // not unrolled on purpose: the generic epilogue is large and eight copies of it thrashed the
-      // instruction cache (ncu r1: 19% of samples stalled on no_inst inside the epilogue)
-#pragma unroll 1
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + (lane >> 3);
-        const int cq = (lane & 7) * 4;
-        const float4 v4 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
-        float v[4] = {v4.x, v4.y, v4.z, v4.w};
-        const int m = m0 + quad * 32 + rr, n = n0 + col0 + cq;
-        if (!split) {
-          epilogue_store4(p.ep, p.C, p.ldc, p.M, p.N, m, n, v);
-        } else if (m < p.M && n < p.Np) {
-          *reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M + m) * p.Np + n) = v4;
-        }
-      }
-      __syncwarp();
+      epilogue_subtile<EPI>(p, stage, m0 + quad * 32, n0 + col0, lane, gridDim.z > 1, blockIdx.z);
     }
     tc_fence_before();
-  } else {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 1u : 0u) << 15) | ((TB ? 0u : 1u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
-        mbar_wait(smem_u32(bars + s), ph);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * C::STAGE), a_lo = a_hi + A_TILE;
-        const uint32_t b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + C::B_TILE;
-#pragma unroll
-        for (int j = 0; j < BK / 8; ++j) {
-          // A: K-major -> advance 32 B inside the swizzle row; MN-major (TA) -> advance one 8-k atom group
-          // (one MMA = 8 k = two 4-k atom groups in the MN-major layout)
-          const uint32_t ao = TA ? (uint32_t)j * 2 * (BM / 32) * 512 : (uint32_t)j * 32;
-          const uint32_t bo = TB ? (uint32_t)j * 32 : (uint32_t)j * 2 * (BN / 32) * 512;
-          const uint32_t a_lbo = TA ? 512 : 16, a_sbo = TA ? (BM / 32) * 512 : 1024, a_lt = TA ? 1u : 2u;
-          const uint32_t b_lbo = TB ? 16 : 512, b_sbo = TB ? 1024 : (BN / 32) * 512, b_lt = TB ? 2u : 1u;
-          const uint64_t dah = make_desc(a_hi + ao, a_lbo, a_sbo, a_lt), dal = make_desc(a_lo + ao, a_lbo, a_sbo, a_lt);
-          const uint64_t dbh = make_desc(b_hi + bo, b_lbo, b_sbo, b_lt), dbl = make_desc(b_lo + bo, b_lbo, b_sbo, b_lt);
-          // The tensor core accumulates in fp32 with truncation, so every accumulation step costs up to one
-          // ulp of the running sum.  The two correction products (2^-11 of the result) go to their own
-          // accumulator: the main one then sees K/8 accumulations instead of 3K/8, and the corrections' own
-          // truncation error is scaled down by 2^-11.  The epilogue adds the two in round-to-nearest.
-          umma_tf32(tmem_base + BN, dal, dbh, idesc, (kb | j) ? 1u : 0u);
-          umma_tf32(tmem_base + BN, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, (kb | j) ? 1u : 0u);
-        }
-        umma_commit(smem_u32(bars + C::STAGES + s));   // frees the stage when these MMAs retire
-      }
-      umma_commit(smem_u32(bars + 2 * C::STAGES));      // accumulator complete
-    }
-    __syncwarp();
+    if (t == 0) TR(5);
   }
   __syncthreads();
-  if (warp == 8) {
+  if (t == 0) TR(6);
+  if (warp == NPW) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, TM_COLS);
   }
 }
 
@@ -339,50 +548,64 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __re
   epilogue_store4(ep, C, ldc, M, N, m, n, v);
 }
 
-struct TcPlan { int bn; int splits; int kps; };
+struct TcPlan { int splits; int kps; };
 
-// Pick the tile width and split-K factor that minimise a simple wave model of the kernel time.
+// Split-K factor from a simple wave model of the kernel time (cycles).  kps <= 1024 caps the truncating fp32
+// accumulation chain of the tensor core at 128 steps per partial.
 TcPlan tc_plan(int M, int N, int K) {
-  const int tm = cdiv(M, BM);
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int nkb = cdiv(K, BK);
-  TcPlan best{128, 1, (int)round_up(K, BK)};
+  TcPlan best{1, (int)round_up(K, BK)};
   double best_cost = 1e300;
-  const int cand_splits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24};
-  for (int bn : {128, 256}) {
-    if (bn == 256 && N <= 128) continue;
-    const int tiles = tm * cdiv(N, bn);
-    for (int sp : cand_splits) {
-      if (sp > 1 && nkb / sp < 4) continue;
-      const int kps = (int)round_up(cdiv(K, sp), BK);
-      if (kps > 1024 && nkb / (sp + 1) >= 4) continue;   // cap the fp32-truncating accumulation chain at 128 steps
-      const int splits = cdiv(K, kps);
-      const int waves = cdiv((int64_t)tiles * splits, 148);
-      const double per_kb = (bn == 256 ? 1536.0 : 768.0 * 1.15);
-      double cost = waves * (cdiv(kps, BK) * per_kb + 2500.0 + bn * 12.0);
-      if (splits > 1) cost += 3000.0 + (double)M * N * (splits + 1) * 4.0 / 4000.0;   // fold kernel (~4 KB/cycle)
-      if (cost < best_cost) { best_cost = cost; best = TcPlan{bn, splits, kps}; }
-    }
+  const int cand_splits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+  for (int sp : cand_splits) {
+    if (sp > 1 && nkb / sp < 4) continue;
+    const int kps = (int)round_up(cdiv(K, sp), BK);
+    if (kps > 1024 && nkb / (sp + 1) >= 4) continue;
+    const int splits = cdiv(K, kps);
+    const int waves = cdiv((int64_t)tiles * splits, 148);
+    double cost = waves * (cdiv(kps, BK) * 800.0 + 3500.0);
+    if (splits > 1) cost += 4000.0 + (double)M * N * (splits + 1) * 4.0 / 4000.0;   // fold kernel (~4 KB/cycle)
+    if (cost < best_cost) { best_cost = cost; best = TcPlan{splits, kps}; }
   }
   return best;
 }
 
-template <int BN>
-int launch_tc(const TcParams& p, bool TA, bool TB, dim3 grid, cudaStream_t st) {
-  constexpr int smem = Cfg<BN>::SMEM;
+template <bool TA, bool TB>
+int launch_tc2(const TcParams& p, int epi, dim3 grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, EPI_DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     attr_done = true;
   }
-  if (!TA && TB) gemm_tc_kernel<BN, false, true><<<grid, NTHREADS, smem, st>>>(p);
-  else if (!TA && !TB) gemm_tc_kernel<BN, false, false><<<grid, NTHREADS, smem, st>>>(p);
-  else if (TA && !TB) gemm_tc_kernel<BN, true, false><<<grid, NTHREADS, smem, st>>>(p);
-  else gemm_tc_kernel<BN, true, true><<<grid, NTHREADS, smem, st>>>(p);
+  if (epi == EPI_PLAIN) gemm_tc_kernel<TA, TB, EPI_PLAIN><<<grid, NTHREADS, SMEM, st>>>(p);
+  else if (epi == EPI_DROP) gemm_tc_kernel<TA, TB, EPI_DROP><<<grid, NTHREADS, SMEM, st>>>(p);
+  else gemm_tc_kernel<TA, TB, EPI_FULL><<<grid, NTHREADS, SMEM, st>>>(p);
   GANFFN_LAUNCHED("gemm_tc_kernel");
   return GANFFN_OK;
+}
+
+int launch_tc(const TcParams& p, bool TA, bool TB, int epi, dim3 grid, cudaStream_t st) {
+  if (!TA && TB) return launch_tc2<false, true>(p, epi, grid, st);
+  if (!TA && !TB) return launch_tc2<false, false>(p, epi, grid, st);
+  if (TA && !TB) return launch_tc2<true, false>(p, epi, grid, st);
+  return launch_tc2<true, true>(p, epi, grid, st);
+}
+
+inline bool al16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
+
+// Which epilogue specialisation can serve this call.
+int pick_epilogue(const Epilogue& ep, const float* C, int ldc, int N) {
+  const bool vec_ok = (N & 3) == 0 && (ldc & 3) == 0 && al16(C) && (!ep.bias || al16(ep.bias)) &&
+                      (!ep.residual || ((ep.ldr & 3) == 0 && al16(ep.residual))) && (!ep.dact_src || al16(ep.dact_src));
+  if (!vec_ok || ep.pre || ep.drop_before_act) return EPI_FULL;
+  if (ep.act == GANFFN_ACT_NONE && ep.p_drop == 0.0f && ep.dact == DACT_NONE) return EPI_PLAIN;
+  if ((ep.act == GANFFN_ACT_NONE || ep.act == GANFFN_ACT_RELU) && (ep.dact == DACT_NONE || ep.dact == DACT_NONZERO) &&
+      !(ep.dact == DACT_NONZERO && (ep.residual || ep.act != GANFFN_ACT_NONE)))
+    return EPI_DROP;
+  return EPI_FULL;
 }
 
 }  // namespace
@@ -391,7 +614,7 @@ bool gemm_tc_supported(bool transA, bool b_is_nk, int lda, int ldb, int ldc, int
                        const void* B) {
   if (M < 96 || N < 64 || K < 32) return false;                       // too small for 128-row tensor tiles
   if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15)) return false;
-  if (transA ? (M & 3) : (K & 3)) return false;                       // 128-bit chunks along the contiguous dim
+  if (!transA && (K & 3)) return false;                               // 128-bit chunks along the contiguous dim
   if (b_is_nk ? (K & 3) : (N & 3)) return false;
   (void)ldc;
   return true;
@@ -414,9 +637,9 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
   TcParams p;
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.M = M; p.N = N; p.K = K; p.k_per_split = pl.kps; p.partial = scratch; p.Np = Np; p.ep = ep;
-  dim3 grid(cdiv(N, pl.bn), cdiv(M, BM), pl.splits);
-  if (pl.bn == 256) GANFFN_TRY(launch_tc<256>(p, transA, b_is_nk, grid, st));
-  else GANFFN_TRY(launch_tc<128>(p, transA, b_is_nk, grid, st));
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), pl.splits);
+  const int epi = pl.splits > 1 ? EPI_PLAIN : pick_epilogue(ep, C, ldc, N);
+  GANFFN_TRY(launch_tc(p, transA, b_is_nk, epi, grid, st));
   if (pl.splits > 1) {
     const int64_t nvec = (int64_t)M * (Np / 4);
     tc_splitk_reduce_kernel<<<cdiv(nvec, 256), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
@@ -426,3 +649,12 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
 }
 
 }  // namespace ganffn
+
+#ifdef GANFFN_TC_TRACE
+extern "C" int ganffn_debug_tc_flags(int f) {
+  return (int)cudaMemcpyToSymbol(ganffn::g_tc_dbg, &f, sizeof(int));
+}
+extern "C" int ganffn_debug_tc_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, ganffn::g_tc_trace, sizeof(long long) * 128);
+}
+#endif
