@@ -1,69 +1,69 @@
-// Self-attention core for whole dialogues: one CTA per (dialogue, head), S <= 110 so a full
-// dialogue's K and V live in shared memory and every thread owns one query (forward) or one
-// query then one key (backward).  Padded slots are real tokens here, exactly as in the
-// reference, which never passes a key-padding mask.
+// Self-attention core for whole dialogues: one CTA per (dialogue, head).  S <= 110, so a dialogue's Q/K/V (and in
+// the backward pass the S x S probability / score-gradient matrices) live in shared memory.  Padded slots are real
+// tokens here, exactly as in the reference, which never passes a key-padding mask.
+//
+// Work decomposition: lane = one row (query, or key in the dK/dV sweeps), warps come in four groups.  In the sweeps
+// over keys (scores, dP) group g owns a quarter of the keys; in the sweeps that produce HD-wide rows (P V, dQ, dK,
+// dV) group g owns a quarter of the output columns, so nothing is reduced across threads.  Every shared-memory
+// operand read is either warp-uniform (broadcast of a K/V/Q/dO row) or walks consecutive floats of an odd-stride
+// S x S row: one wavefront per instruction.  (A first version with one thread per query and no groups had 3 warps
+// per CTA and ran latency-bound: 26/100 us fwd/bwd per d=100 layer at S=94, B=32.)
 #include "common.cuh"
 
 namespace ganffn {
 namespace {
 
-constexpr int ATT_THREADS = 128;  // >= GANFFN_MAX_SEQ
+constexpr int NG = 4;                                // warp groups
+constexpr int MAX_RW = (GANFFN_MAX_SEQ + 31) / 32;   // row warps per group
+constexpr int KPG = ((GANFFN_MAX_SEQ + 4 * NG - 1) / (4 * NG)) * 4;   // max keys per group (multiple of 4)
 
 template <int HD>
-struct Vec {
-  static constexpr int W = (HD % 4 == 0) ? 4 : (HD % 2 == 0) ? 2 : 1;
+struct Cfg {
+  static constexpr int W = (HD % 4 == 0) ? 4 : (HD % 2 == 0) ? 2 : 1;   // vector width of a row
+  static constexpr int CW = (HD + NG - 1) / NG;                          // output columns per group
+  static constexpr int CWV = (CW % 4 == 0) ? 4 : 1;
 };
-
-template <int HD>
-__device__ __forceinline__ void load_row(const float* __restrict__ g, float* r) {
-  constexpr int W = Vec<HD>::W;
-  if (W == 4) {
-#pragma unroll
-    for (int c = 0; c < HD / 4; ++c) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(g) + c);
-      r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
-    }
-  } else if (W == 2) {
-#pragma unroll
-    for (int c = 0; c < HD / 2; ++c) {
-      float2 v = __ldg(reinterpret_cast<const float2*>(g) + c);
-      r[2 * c] = v.x; r[2 * c + 1] = v.y;
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < HD; ++c) r[c] = __ldg(g + c);
-  }
-}
-
-template <int HD>
-__device__ __forceinline__ void store_row(float* g, const float* r) {
-  constexpr int W = Vec<HD>::W;
-  if (W == 4) {
-#pragma unroll
-    for (int c = 0; c < HD / 4; ++c)
-      reinterpret_cast<float4*>(g)[c] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-  } else if (W == 2) {
-#pragma unroll
-    for (int c = 0; c < HD / 2; ++c) reinterpret_cast<float2*>(g)[c] = make_float2(r[2 * c], r[2 * c + 1]);
-  } else {
-#pragma unroll
-    for (int c = 0; c < HD; ++c) g[c] = r[c];
-  }
-}
 
 // Cooperative copy of one head's [S, HD] slice (row stride `ld` floats in global) to smem [S][HD].
 template <int HD>
 __device__ __forceinline__ void load_tile(const float* __restrict__ g, int ld, float* s, int S) {
-  for (int idx = threadIdx.x; idx < S * HD; idx += blockDim.x) {
-    int r = idx / HD, c = idx % HD;
-    s[idx] = __ldg(g + (size_t)r * ld + c);
+  constexpr int W = Cfg<HD>::W, CPR = HD / W;
+  for (int idx = threadIdx.x; idx < S * CPR; idx += blockDim.x) {
+    const int r = idx / CPR, c = (idx % CPR) * W;
+    const float* src = g + (size_t)r * ld + c;
+    float* dst = s + r * HD + c;
+    if (W == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+    else if (W == 2) *reinterpret_cast<float2*>(dst) = __ldg(reinterpret_cast<const float2*>(src));
+    else *dst = __ldg(src);
   }
 }
 
 template <int HD>
+__device__ __forceinline__ void row_to_regs(const float* __restrict__ s, float* r, float mul) {
+  constexpr int W = Cfg<HD>::W;
+  if (W == 4) {
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(s + 4 * c);
+      r[4 * c] = v.x * mul; r[4 * c + 1] = v.y * mul; r[4 * c + 2] = v.z * mul; r[4 * c + 3] = v.w * mul;
+    }
+  } else if (W == 2) {
+#pragma unroll
+    for (int c = 0; c < HD / 2; ++c) {
+      const float2 v = *reinterpret_cast<const float2*>(s + 2 * c);
+      r[2 * c] = v.x * mul; r[2 * c + 1] = v.y * mul;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; ++c) r[c] = s[c] * mul;
+  }
+}
+
+// q (registers) . row (warp-uniform smem address)
+template <int HD>
 __device__ __forceinline__ float dot_smem(const float* q, const float* __restrict__ krow) {
   float s = 0.f;
-  constexpr int W = Vec<HD>::W;
+  constexpr int W = Cfg<HD>::W;
   if (W == 4) {
 #pragma unroll
     for (int c = 0; c < HD / 4; ++c) {
@@ -84,100 +84,146 @@ __device__ __forceinline__ float dot_smem(const float* q, const float* __restric
   return s;
 }
 
+// acc[0..CW) += a * row[c0 .. c0+CW)  (warp-uniform row; columns past HD are skipped)
 template <int HD>
-__device__ __forceinline__ void axpy_smem(float a, const float* __restrict__ row, float* acc) {
-  constexpr int W = Vec<HD>::W;
-  if (W == 4) {
+__device__ __forceinline__ void axpy_cols(float a, const float* __restrict__ row, int c0, float* acc) {
+  constexpr int CW = Cfg<HD>::CW;
+  if (Cfg<HD>::CWV == 4) {
 #pragma unroll
-    for (int c = 0; c < HD / 4; ++c) {
-      float4 v = *reinterpret_cast<const float4*>(row + 4 * c);
+    for (int c = 0; c < CW / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c0 + 4 * c);
       acc[4 * c] = fmaf(a, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(a, v.y, acc[4 * c + 1]);
       acc[4 * c + 2] = fmaf(a, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(a, v.w, acc[4 * c + 3]);
     }
-  } else if (W == 2) {
-#pragma unroll
-    for (int c = 0; c < HD / 2; ++c) {
-      float2 v = *reinterpret_cast<const float2*>(row + 2 * c);
-      acc[2 * c] = fmaf(a, v.x, acc[2 * c]); acc[2 * c + 1] = fmaf(a, v.y, acc[2 * c + 1]);
-    }
   } else {
 #pragma unroll
-    for (int c = 0; c < HD; ++c) acc[c] = fmaf(a, row[c], acc[c]);
+    for (int c = 0; c < CW; ++c)
+      if (c0 + c < HD) acc[c] = fmaf(a, row[c0 + c], acc[c]);
   }
+}
+
+template <int HD>
+__device__ __forceinline__ void store_cols(float* g, int c0, const float* acc, float mul) {
+  constexpr int CW = Cfg<HD>::CW;
+  if (Cfg<HD>::CWV == 4) {
+#pragma unroll
+    for (int c = 0; c < CW / 4; ++c)
+      *reinterpret_cast<float4*>(g + c0 + 4 * c) =
+          make_float4(acc[4 * c] * mul, acc[4 * c + 1] * mul, acc[4 * c + 2] * mul, acc[4 * c + 3] * mul);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CW; ++c)
+      if (c0 + c < HD) g[c0 + c] = acc[c] * mul;
+  }
+}
+
+// Sweep producing an HD-wide row per lane: acc = sum_r M[r][row] or M[row][r] (see callers) * X[r][c0..c0+CW).
+// `m` points at the lane's first coefficient, `mstride` is the step between consecutive r.
+template <int HD>
+__device__ __forceinline__ void sweep_cols(const float* __restrict__ m, int mstride, const float* __restrict__ X, int S,
+                                           int c0, float* acc) {
+#pragma unroll
+  for (int c = 0; c < Cfg<HD>::CW; ++c) acc[c] = 0.f;
+  int r = 0;
+  for (; r + 4 <= S; r += 4) {
+    const float a0 = m[(r + 0) * mstride], a1 = m[(r + 1) * mstride], a2 = m[(r + 2) * mstride], a3 = m[(r + 3) * mstride];
+    axpy_cols<HD>(a0, X + (r + 0) * HD, c0, acc);
+    axpy_cols<HD>(a1, X + (r + 1) * HD, c0, acc);
+    axpy_cols<HD>(a2, X + (r + 2) * HD, c0, acc);
+    axpy_cols<HD>(a3, X + (r + 3) * HD, c0, acc);
+  }
+  for (; r < S; ++r) axpy_cols<HD>(m[r * mstride], X + r * HD, c0, acc);
 }
 
 // ---- forward ----------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o,
-                                                                    float* __restrict__ lse, int S, int B, int d,
-                                                                    int nhead, float p_drop, uint64_t seed,
-                                                                    uint32_t site) {
+__global__ void __launch_bounds__(NG * MAX_RW * 32) attention_fwd_kernel(const float* __restrict__ qkv,
+                                                                         float* __restrict__ o, float* __restrict__ lse,
+                                                                         int S, int B, int d, int nhead, float p_drop,
+                                                                         uint64_t seed, uint32_t site) {
   extern __shared__ __align__(16) float smem[];
-  float* Ks = smem;            // [S][HD]
-  float* Vs = smem + S * HD;   // [S][HD]
+  const int SP = S | 1;
+  float* Qs = smem;              // [S][HD]
+  float* Ks = Qs + S * HD;
+  float* Vs = Ks + S * HD;
+  float* Ps = Vs + S * HD;       // [S][SP] dropped probabilities, not yet normalised
+  float* red = Ps + S * SP;      // [NG][S] partial row max, then partial row sums
   const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
-  const int ld = B * 3 * d;    // row stride between consecutive s for fixed b
+  const int ld = B * 3 * d;      // row stride between consecutive s for fixed b
   const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
+  load_tile<HD>(base, ld, Qs, S);
   load_tile<HD>(base + d, ld, Ks, S);
   load_tile<HD>(base + 2 * d, ld, Vs, S);
   __syncthreads();
 
-  const int i = threadIdx.x;
-  if (i >= S) return;
+  const int nrw = (S + 31) >> 5;                       // row warps per group
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = warp / nrw, i = (warp % nrw) * 32 + lane;
+  const bool active = i < S;
+  const int ir = active ? i : S - 1;
+  const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;  // keys per group, multiple of 4
+  const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
   const float scale = rsqrtf((float)HD);
-  float q[HD], acc[HD];
-  load_row<HD>(base + (size_t)i * ld, q);
-#pragma unroll
-  for (int c = 0; c < HD; ++c) { q[c] *= scale; acc[c] = 0.f; }
 
+  float s[KPG];
+  float mx = -INFINITY;
+  {
+    float q[HD];
+    row_to_regs<HD>(Qs + ir * HD, q, scale);
+#pragma unroll
+    for (int k = 0; k < KPG; ++k) {
+      const int j = j_beg + k;
+      s[k] = (j < j_end) ? dot_smem<HD>(q, Ks + j * HD) : -INFINITY;
+      mx = fmaxf(mx, s[k]);
+    }
+  }
+  red[g * S + ir] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[ir], red[S + ir]), fmaxf(red[2 * S + ir], red[3 * S + ir]));
+  __syncthreads();
   const bool drop = p_drop > 0.f;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int S4 = (S + 3) & ~3;
-  const uint64_t ebase = ((uint64_t)blockIdx.x * S + i) * S4;
-
-  float mrun = -INFINITY, lrun = 0.f;
-  for (int j0 = 0; j0 < S; j0 += 8) {
-    float s[8];
-    float cmax = -INFINITY;
+  const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
+  float lsum = 0.f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      s[u] = (j < S) ? dot_smem<HD>(q, Ks + j * HD) : -INFINITY;
-      cmax = fmaxf(cmax, s[u]);
-    }
-    const float mnew = fmaxf(mrun, cmax);
-    const float corr = __expf(mrun - mnew);  // 0 on the first chunk
-    lrun *= corr;
+  for (int k4 = 0; k4 < KPG; k4 += 4) {
+    const int j0 = j_beg + k4;
+    if (j0 < j_end) {
+      float msk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop) dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
 #pragma unroll
-    for (int c = 0; c < HD; ++c) acc[c] *= corr;
-    float msk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-    if (drop) {
-      dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
-      dropout_scale4(seed, site, ebase + j0 + 4, p_drop, dscale, msk + 4);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      if (j < S) {
-        const float pj = expf(s[u] - mnew);
-        lrun += pj;
-        axpy_smem<HD>(pj * msk[u], Vs + j * HD, acc);
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < j_end) {
+          const float pj = expf(s[k4 + u] - mx);
+          lsum += pj;
+          if (active) Ps[i * SP + j0 + u] = pj * msk[u];
+        }
       }
     }
-    mrun = mnew;
   }
-  const float inv = 1.f / lrun;
-#pragma unroll
-  for (int c = 0; c < HD; ++c) acc[c] *= inv;
-  store_row<HD>(o + ((size_t)i * B + b) * d + (size_t)h * HD, acc);
-  lse[(size_t)blockIdx.x * S + i] = mrun + logf(lrun);
+  red[g * S + ir] = lsum;
+  __syncthreads();
+  lsum = (red[ir] + red[S + ir]) + (red[2 * S + ir] + red[3 * S + ir]);
+
+  // O_i[c0 .. c0+CW) = sum_j P_ij V_j[c0 ..): group g now owns a quarter of the columns
+  constexpr int CW = Cfg<HD>::CW;
+  const int c0 = g * CW;
+  float acc[CW];
+  sweep_cols<HD>(Ps + ir * SP, 1, Vs, S, c0, acc);
+  if (active) {
+    store_cols<HD>(o + ((size_t)i * B + b) * d + (size_t)h * HD, c0, acc, 1.f / lsum);
+    if (g == 0) lse[(size_t)blockIdx.x * S + i] = mx + logf(lsum);
+  }
 }
 
 // ---- backward ---------------------------------------------------------------------------------
-// Phase A (thread = query i): recompute P row, dS row; dQ_i; park Pd and dS in smem.
-// Phase B (thread = key j):   dV_j = sum_i Pd[i][j] dO_i ; dK_j = sum_i dS[i][j] Q_i.
+//   lane = query i, group = key range:   P_ij = exp(q_i.k_j - lse_i);  dP_ij = dO_i.v_j;
+//                                        Ps = P m,  dSs = P (dP m - D_i) scale
+//   lane = query i, group = columns:     dQ_i = sum_j dSs_ij k_j
+//   lane = key j,   group = columns:     dV_j = sum_i Ps_ij dO_i ;  dK_j = sum_i dSs_ij q_i
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(
+__global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
     const float* __restrict__ d_o, float* __restrict__ dqkv, int S, int B, int d, int nhead, float p_drop,
     uint64_t seed, uint32_t site) {
@@ -203,8 +249,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(
   load_tile<HD>(dobase, ldo, dOs, S);
   __syncthreads();
   {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = w; r < S; r += ATT_THREADS / 32) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = w; r < S; r += nw) {
       float acc = 0.f;
       for (int c = lane; c < HD; c += 32) acc += dOs[r * HD + c] * __ldg(obase + (size_t)r * ldo + c);
       acc = warp_sum(acc);
@@ -213,69 +259,67 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(
   }
   __syncthreads();
 
+  const int nrw = (S + 31) >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = warp / nrw, i = (warp % nrw) * 32 + lane;
+  const bool active = i < S;
+  const int ir = active ? i : S - 1;
+  const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;
+  const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
   const float scale = rsqrtf((float)HD);
   const bool drop = p_drop > 0.f;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int S4 = (S + 3) & ~3;
-  const int i = threadIdx.x;
+  const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
 
-  if (i < S) {
-    float q[HD], g[HD], dq[HD];
-#pragma unroll
-    for (int c = 0; c < HD; ++c) { q[c] = Qs[i * HD + c] * scale; g[c] = dOs[i * HD + c]; dq[c] = 0.f; }
+  if (active) {
+    float r[HD];
     const float li = lse[(size_t)blockIdx.x * S + i];
+    row_to_regs<HD>(Qs + i * HD, r, scale);
+    for (int j = j_beg; j < j_end; ++j) Ps[i * SP + j] = expf(dot_smem<HD>(r, Ks + j * HD) - li);
+    row_to_regs<HD>(dOs + i * HD, r, 1.f);
     const float Di = Dv[i];
-    const uint64_t ebase = ((uint64_t)blockIdx.x * S + i) * S4;
-    for (int j0 = 0; j0 < S; j0 += 4) {
+    for (int j0 = j_beg; j0 < j_end; j0 += 4) {
       float msk[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop) dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = j0 + u;
-        if (j < S) {
-          const float s = dot_smem<HD>(q, Ks + j * HD);
-          const float pj = expf(s - li);
-          const float dpd = dot_smem<HD>(g, Vs + j * HD);
-          const float ds = pj * (dpd * msk[u] - Di);
+        if (j < j_end) {
+          const float pj = Ps[i * SP + j];
+          const float dpd = dot_smem<HD>(r, Vs + j * HD);
           Ps[i * SP + j] = pj * msk[u];
-          dSs[i * SP + j] = ds * scale;
-          axpy_smem<HD>(ds, Ks + j * HD, dq);
+          dSs[i * SP + j] = pj * (dpd * msk[u] - Di) * scale;
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < HD; ++c) dq[c] *= scale;
-    store_row<HD>(dqkv + ((size_t)i * B + b) * 3 * d + (size_t)h * HD, dq);
   }
   __syncthreads();
-  if (i < S) {
-    const int j = i;
-    float dk[HD], dv[HD];
-#pragma unroll
-    for (int c = 0; c < HD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-    for (int r = 0; r < S; ++r) {
-      const float pd = Ps[r * SP + j];
-      const float ds = dSs[r * SP + j];
-      axpy_smem<HD>(pd, dOs + r * HD, dv);
-      axpy_smem<HD>(ds, Qs + r * HD, dk);
-    }
-    float* out = dqkv + ((size_t)j * B + b) * 3 * d + (size_t)h * HD;
-    store_row<HD>(out + d, dk);
-    store_row<HD>(out + 2 * d, dv);
-  }
+
+  constexpr int CW = Cfg<HD>::CW;
+  const int c0 = g * CW;
+  float acc[CW];
+  float* out = dqkv + ((size_t)ir * B + b) * 3 * d + (size_t)h * HD;
+  sweep_cols<HD>(dSs + ir * SP, 1, Ks, S, c0, acc);        // dQ_i (row i of dSs)
+  if (active) store_cols<HD>(out, c0, acc, 1.f);
+  sweep_cols<HD>(Ps + ir, SP, dOs, S, c0, acc);            // dV_j (column j = ir of Ps)
+  if (active) store_cols<HD>(out + 2 * d, c0, acc, 1.f);
+  sweep_cols<HD>(dSs + ir, SP, Qs, S, c0, acc);            // dK_j (column j of dSs)
+  if (active) store_cols<HD>(out + d, c0, acc, 1.f);
 }
+
+inline int att_threads(int S) { return NG * ((S + 31) / 32) * 32; }
 
 template <int HD>
 int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, uint64_t seed, int site,
                cudaStream_t st) {
-  const size_t smem = (size_t)2 * S * HD * sizeof(float);
+  auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)s * (s | 1) + (size_t)NG * s) * sizeof(float); };
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(2 * GANFFN_MAX_SEQ * HD * sizeof(float)));
+    cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(GANFFN_MAX_SEQ));
     attr_done = true;
   }
-  attention_fwd_kernel<HD><<<B * nhead, ATT_THREADS, smem, st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
+  attention_fwd_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
   GANFFN_LAUNCHED("attention_fwd_kernel");
   return GANFFN_OK;
 }
@@ -290,8 +334,8 @@ int launch_bwd(const float* qkv, const float* o, const float* lse, const float* 
                          (int)bytes(GANFFN_MAX_SEQ));
     attr_done = true;
   }
-  attention_bwd_kernel<HD><<<B * nhead, ATT_THREADS, bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
-                                                                    (uint32_t)site);
+  attention_bwd_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
+                                                                       (uint32_t)site);
   GANFFN_LAUNCHED("attention_bwd_kernel");
   return GANFFN_OK;
 }

@@ -1,12 +1,15 @@
-"""Times every GEMM shape of the IEMOCAP train step (T=3008) on both engines with CUDA events.
+"""Times every GEMM shape of the IEMOCAP train step (T=3008) on both engines (CUDA-graph replay of 20 back-to-back
+calls, so host launch overhead is excluded and L2 is warm, as inside the step).
 Not a benchmark of the step: a tuning aid.  Output: one line per (kind, M, N, K, engine)."""
 import ctypes
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 import torch  # noqa: E402
 from gan_ffn_b200._lib import lib  # noqa: E402
+from gtime import graph_time  # noqa: E402
 
 L = lib()
 T = int(os.environ.get("T", 3008))
@@ -19,8 +22,6 @@ for d, name in ((512, "Gv"), (100, "d100")):
         shapes.append((f"{name}.{tag}.dgrad", "dgrad", T, n, k))
         shapes.append((f"{name}.{tag}.wgrad", "wgrad", T, n, k))
 shapes += [("Gv.fc1.fwd", "fwd", T, 1024, 512), ("Gv.fc2.fwd", "fwd", T, 100, 1024), ("d100.fc1.fwd", "fwd", T, 512, 100)]
-st = torch.cuda.current_stream().cuda_stream
-flush = torch.empty(64 * 1024 * 1024, device=dev)
 
 
 def run(kind, M, N, K, engine, iters=20):
@@ -35,6 +36,7 @@ def run(kind, M, N, K, engine, iters=20):
                          int(L.cdll.ganffn_wgrad_scratch_floats(M, N, K)), 1), device=dev)
 
     def call():
+        st = torch.cuda.current_stream().cuda_stream
         if kind == "fwd":
             L.call("ganffn_linear_fwd", x.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), None, M, N, K, 0, 0, 0.0, 0, 0,
                    ws.data_ptr(), ws.numel(), st)
@@ -42,16 +44,7 @@ def run(kind, M, N, K, engine, iters=20):
             L.call("ganffn_linear_dgrad", dy.data_ptr(), w.data_ptr(), None, dx.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(), st)
         else:
             L.call("ganffn_linear_wgrad", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), None, M, N, K, 0, ws.data_ptr(), st)
-    for _ in range(3):
-        call()
-    tot = 0.0
-    for _ in range(iters):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); call(); b.record()
-        torch.cuda.synchronize()
-        tot += a.elapsed_time(b)
-    return tot / iters
+    return graph_time(call) * 1e-3
 
 
 print(f"{'shape':24s} {'M':>5s} {'N':>5s} {'K':>5s}  simt_us  simt_TF    tc_us    tc_TF")
