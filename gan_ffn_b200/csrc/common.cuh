@@ -135,6 +135,11 @@ struct Epilogue {
   const float* dact_src = nullptr;  // [M, ldc]
   float dact_scale = 1.0f;          // DACT_NONZERO: multiply kept lanes by this (1/(1-p))
   float beta = 0.0f;                // C = beta*C + v
+  // Gradient accumulation (wgrad): C += v with red.global.add, so split-K slices need no partial buffers and no
+  // fold kernel; the tcgen05 engine can also emit rowsum[m] += sum_k A[m,k] (the bias gradient, since A = dY^T)
+  // from the registers of its A producers.  The FFMA engine treats `atomic_acc` as beta = 1 and ignores `rowsum`.
+  int atomic_acc = 0;
+  float* rowsum = nullptr;
 };
 
 // Applies the epilogue to the four accumulators of row m, columns n..n+3 (n % 4 == 0) and
@@ -205,5 +210,7 @@ __device__ __forceinline__ void epilogue_store4(const Epilogue& ep, float* C, in
 int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
          int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st);
 int64_t gemm_scratch_floats(int M, int N, int K);
+// true when gemm() would run this product on the tcgen05 engine (which honours Epilogue::rowsum)
+bool gemm_uses_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, int ldc, int M, int N, int K);
 
 }  // namespace ganffn

@@ -65,6 +65,7 @@ struct TcParams {
   int M, N, K;
   int k_per_split;   // multiple of BK
   float* partial; int Np;
+  int out_mode;      // 0 fused epilogue, 1 split-K partials, 2 red.global.add (vector), 3 red.global.add (scalar)
   Epilogue ep;
 };
 
@@ -149,6 +150,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 
+// Explicit shared-space accesses: the dynamic smem base goes through integer alignment arithmetic, after which the
+// compiler only knows a generic pointer and would emit generic LD/ST (seen in SASS as ST.E.128 / LD.E.128).
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // A operand from tensor memory (".ts"): lanes = rows of the tile, one tf32 per 32-bit column.
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -217,8 +229,10 @@ __device__ __forceinline__ void quad_transpose(float (&v)[16], int lane) {
 }
 
 template <bool KMAJ>
-__device__ __forceinline__ void store_a(float (&v)[16], uint32_t taddr_hi, int lane) {
-  if (KMAJ && !DBG(4)) quad_transpose(v, lane);
+__device__ __forceinline__ void store_a(float (&v)[16], uint32_t taddr_hi, int lane, float& rowsum) {
+  if (KMAJ) quad_transpose(v, lane);
+  rowsum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) + ((v[8] + v[9]) + (v[10] + v[11])) +
+            ((v[12] + v[13]) + (v[14] + v[15]));
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -255,7 +269,7 @@ __device__ __forceinline__ void load_b(float4 (&v)[BCH], const float* __restrict
 }
 
 template <bool KMAJ>
-__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint8_t* hi, uint8_t* lo, int tb) {
+__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uint32_t lo, int tb) {
 #pragma unroll
   for (int i = 0; i < BCH; ++i) {
     const int q = tb + i * NB;
@@ -276,26 +290,49 @@ __device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint8_t* hi, uin
       h[j] = tf32_rna(x[j]);
       l[j] = tf32_rna(x[j] - __uint_as_float(h[j]));
     }
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    sts128(hi + off, h[0], h[1], h[2], h[3]);
+    sts128(lo + off, l[0], l[1], l[2], l[3]);
   }
 }
 
 // ---- epilogue of one 32 x 32 sub-tile (already transposed into `stage`, 32 rows x 36 floats) ------------------------
 // Lane -> rows i8*4 + lane/8 (i8 = 0..7), columns (lane%8)*4 .. +3: every global access is a 128-byte row segment.
 template <int EPI>
-__device__ __forceinline__ void epilogue_subtile(const TcParams& p, const float* stage, int m_base, int n_base, int lane,
-                                                 bool split, int z) {
+__device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t stage, int m_base, int n_base, int lane,
+                                                 int z) {
   const int cq = (lane & 7) * 4, r0 = lane >> 3;
   const int n = n_base + cq;
-  if (split) {
+  // All loops below stay rolled on purpose: this code runs once per CTA, so its cost is instruction fetch, not
+  // issue (r1 timeline: 3700 cycles for the fully unrolled version of 8 x {LDS, 4 FADD, STG}; the instruction
+  // cache is cold at every launch).
+  if (p.out_mode >= 2) {   // gradient accumulation: C += tile
+    if (n < p.N) {
+#pragma unroll 1
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int rr = i8 * 4 + r0, m = m_base + rr;
+        if (m < p.M) {
+          const float4 v = lds128(stage + (uint32_t)(rr * 36 + cq) * 4);
+          float* c = p.C + (size_t)m * p.ldc + n;
+          if (p.out_mode == 2) {
+            atomicAdd(reinterpret_cast<float4*>(c), v);
+          } else {
+            atomicAdd(c, v.x);
+            if (n + 1 < p.N) atomicAdd(c + 1, v.y);
+            if (n + 2 < p.N) atomicAdd(c + 2, v.z);
+            if (n + 3 < p.N) atomicAdd(c + 3, v.w);
+          }
+        }
+      }
+    }
+    return;
+  }
+  if (p.out_mode == 1) {
     if (n < p.Np) {
-#pragma unroll
+#pragma unroll 1
       for (int i8 = 0; i8 < 8; ++i8) {
         const int rr = i8 * 4 + r0, m = m_base + rr;
         if (m < p.M)
-          *reinterpret_cast<float4*>(p.partial + ((size_t)z * p.M + m) * p.Np + n) =
-              *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+          *reinterpret_cast<float4*>(p.partial + ((size_t)z * p.M + m) * p.Np + n) = lds128(stage + (uint32_t)(rr * 36 + cq) * 4);
       }
     }
     return;
@@ -304,7 +341,7 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, const float*
 #pragma unroll 1
     for (int i8 = 0; i8 < 8; ++i8) {
       const int rr = i8 * 4 + r0;
-      const float4 v4 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+      const float4 v4 = lds128(stage + (uint32_t)(rr * 36 + cq) * 4);
       float v[4] = {v4.x, v4.y, v4.z, v4.w};
       epilogue_store4(p.ep, p.C, p.ldc, p.M, p.N, m_base + rr, n, v);
     }
@@ -317,28 +354,31 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, const float*
   if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
   const float* aux_base = ep.residual ? ep.residual : (EPI == EPI_DROP && ep.dact == DACT_NONZERO ? ep.dact_src : nullptr);
   const int aux_ld = ep.residual ? ep.ldr : p.ldc;
-  float4 aux[8], old[8];
-#pragma unroll
-  for (int i8 = 0; i8 < 8; ++i8) {
-    const int m = m_base + i8 * 4 + r0;
-    aux[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
-    old[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < p.M) {
-      if (aux_base) aux[i8] = *reinterpret_cast<const float4*>(aux_base + (size_t)m * aux_ld + n);
-      if (ep.beta != 0.0f) old[i8] = *reinterpret_cast<const float4*>(p.C + (size_t)m * p.ldc + n);
-    }
-  }
+  const bool has_beta = ep.beta != 0.0f;
   const bool relu = EPI == EPI_DROP && ep.act == GANFFN_ACT_RELU;
   const bool drop = EPI == EPI_DROP && ep.p_drop > 0.0f && ep.dact == DACT_NONE;
   const bool dnz = EPI == EPI_DROP && ep.dact == DACT_NONZERO;
   const float dscale = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
-#pragma unroll
+  // software pipeline: the residual / dact source / old C of row group i8+1 is in flight while i8 is computed
+  float4 aux_n = make_float4(0.f, 0.f, 0.f, 0.f), old_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int i8) {
+    const int m = m_base + i8 * 4 + r0;
+    if (m < p.M) {
+      if (aux_base) aux_n = *reinterpret_cast<const float4*>(aux_base + (size_t)m * aux_ld + n);
+      if (has_beta) old_n = *reinterpret_cast<const float4*>(p.C + (size_t)m * p.ldc + n);
+    }
+  };
+  prefetch(0);
+#pragma unroll 1
   for (int i8 = 0; i8 < 8; ++i8) {
     const int rr = i8 * 4 + r0, m = m_base + rr;
+    if (threadIdx.x == 0) TR(73 + i8);
+    const float4 aux4 = aux_n, old4 = old_n;
+    if (i8 + 1 < 8) prefetch(i8 + 1);
     if (m >= p.M) continue;
-    const float4 a4 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+    const float4 a4 = lds128(stage + (uint32_t)(rr * 36 + cq) * 4);
     float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
-    const float ax[4] = {aux[i8].x, aux[i8].y, aux[i8].z, aux[i8].w};
+    const float ax[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
     if (relu) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.0f;
@@ -356,8 +396,8 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += ax[j];   // residual (zeros when absent)
     }
-    if (ep.beta != 0.0f) {
-      v[0] += ep.beta * old[i8].x; v[1] += ep.beta * old[i8].y; v[2] += ep.beta * old[i8].z; v[3] += ep.beta * old[i8].w;
+    if (has_beta) {
+      v[0] += ep.beta * old4.x; v[1] += ep.beta * old4.y; v[2] += ep.beta * old4.z; v[3] += ep.beta * old4.w;
     }
     *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -403,50 +443,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
     const int row_base = m0 + quad * 32;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TM_A + half * 16);
     float buf[RING][16];
-#pragma unroll
-    for (int r = 0; r < RING; ++r)
-      if (r < nkb) load_a<!TA>(buf[r], p.A, p.lda, row_base, lane, p.M, kbeg + r * BK + half * 16, kend);
-    for (int kb0 = 0; kb0 < nkb; kb0 += RING) {
+    float rowsum = 0.f;   // sum over this thread's k of its A row (bias gradient of a wgrad product)
+    // kb0 starts at -RING: the first pass only issues the loads of K blocks 0..RING-1 (same code as steady state,
+    // so nothing here is executed-once straight-line code)
+    for (int kb0 = -RING; kb0 < nkb; kb0 += RING) {
 #pragma unroll
       for (int r = 0; r < RING; ++r) {
         const int kb = kb0 + r;
-        if (kb < nkb) {
+        if (kb >= 0 && kb < nkb) {
           const int s = kb % STAGES;
           const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
           mbar_wait(smem_u32(empty + s), ph ^ 1u);
           tc_fence_after();
-          if (!DBG(1)) store_a<!TA>(buf[r], trow + (uint32_t)(s * 64), lane);
+          store_a<!TA>(buf[r], trow + (uint32_t)(s * 64), lane, rowsum);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full + s));
-          if (kb + RING < nkb) load_a<!TA>(buf[r], p.A, p.lda, row_base, lane, p.M, kbeg + (kb + RING) * BK + half * 16, kend);
           if (t == 0 && kb < 16) TR(8 + kb);
         }
+        if (kb + RING < nkb) load_a<!TA>(buf[r], p.A, p.lda, row_base, lane, p.M, kbeg + (kb + RING) * BK + half * 16, kend);
       }
     }
+    if (p.ep.rowsum != nullptr && blockIdx.x == 0 && row_base + lane < p.M) atomicAdd(p.ep.rowsum + row_base + lane, rowsum);
   } else if (warp < NPW) {
     // ================= B producers: global -> registers -> shared memory =================
     const int tb = t - NAW * 32;
     float4 buf[RING][BCH];
-#pragma unroll
-    for (int r = 0; r < RING; ++r)
-      if (r < nkb) load_b<TB>(buf[r], p.B, p.ldb, n0, p.N, kbeg + r * BK, kend, tb);
-    for (int kb0 = 0; kb0 < nkb; kb0 += RING) {
+    for (int kb0 = -RING; kb0 < nkb; kb0 += RING) {
 #pragma unroll
       for (int r = 0; r < RING; ++r) {
         const int kb = kb0 + r;
-        if (kb < nkb) {
+        if (kb >= 0 && kb < nkb) {
           const int s = kb % STAGES;
           const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
           mbar_wait(smem_u32(empty + s), ph ^ 1u);
-          uint8_t* st = smem + s * STAGE;
-          if (!DBG(2)) store_b<TB>(buf[r], st, st + B_TILE, tb);
+          const uint32_t st = smem_u32(smem) + (uint32_t)(s * STAGE);
+          store_b<TB>(buf[r], st, st + B_TILE, tb);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full + s));
-          if (kb + RING < nkb) load_b<TB>(buf[r], p.B, p.ldb, n0, p.N, kbeg + (kb + RING) * BK, kend, tb);
           if (tb == 0 && kb < 16) TR(24 + kb);
         }
+        if (kb + RING < nkb) load_b<TB>(buf[r], p.B, p.ldb, n0, p.N, kbeg + (kb + RING) * BK, kend, tb);
       }
     }
   } else {
@@ -504,23 +542,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
     if (t == 0) TR(4);
     const int quad = warp & 3, col0 = (warp >> 2) * 32;
     if (nkb > 0 && n0 + col0 < p.N) {
-      float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);   // private 32 x 36 fp32 transpose buffer
+      const uint32_t stage = smem_u32(smem) + (uint32_t)(warp * (32 * 36) * 4);   // private 32 x 36 fp32 transpose buffer
       uint32_t r[32], rl[32];
       const uint32_t tr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
       tmem_ld32(tr + TM_MAIN, r);
       tmem_ld32(tr + TM_CORR, rl);
       tmem_ld_wait();
+      if (t == 0) TR(70);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float4 o;
-        o.x = __uint_as_float(r[4 * q]) + __uint_as_float(rl[4 * q]);
-        o.y = __uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]);
-        o.z = __uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]);
-        o.w = __uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]);
-        *reinterpret_cast<float4*>(stage + lane * 36 + q * 4) = o;
+        const float ox = __uint_as_float(r[4 * q]) + __uint_as_float(rl[4 * q]);
+        const float oy = __uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]);
+        const float oz = __uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]);
+        const float ow = __uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]);
+        sts128(stage + (uint32_t)(lane * 36 + q * 4) * 4, __float_as_uint(ox), __float_as_uint(oy), __float_as_uint(oz),
+               __float_as_uint(ow));
       }
       __syncwarp();
-      epilogue_subtile<EPI>(p, stage, m0 + quad * 32, n0 + col0, lane, gridDim.z > 1, blockIdx.z);
+      if (t == 0) TR(71);
+      epilogue_subtile<EPI>(p, stage, m0 + quad * 32, n0 + col0, lane, blockIdx.z);
+      if (t == 0) TR(72);
     }
     tc_fence_before();
     if (t == 0) TR(5);
@@ -549,6 +590,24 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __re
 }
 
 struct TcPlan { int splits; int kps; };
+
+// Split-K for an accumulating (red.global.add) product: no fold kernel, so the only costs are the per-CTA
+// prologue / atomic epilogue and the waves.
+TcPlan tc_plan_atomic(int M, int N, int K) {
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int nkb = cdiv(K, BK);
+  TcPlan best{1, (int)round_up(K, BK)};
+  double best_cost = 1e300;
+  for (int sp = 1; sp <= nkb && sp <= 64; ++sp) {
+    const int kps = (int)round_up(cdiv(K, sp), BK);
+    if (kps > 1024) continue;
+    const int splits = cdiv(K, kps);
+    const int waves = cdiv((int64_t)tiles * splits, 148);
+    const double cost = waves * (cdiv(kps, BK) * 800.0 + 6000.0) + splits * 150.0;
+    if (cost < best_cost) { best_cost = cost; best = TcPlan{splits, kps}; }
+  }
+  return best;
+}
 
 // Split-K factor from a simple wave model of the kernel time (cycles).  kps <= 1024 caps the truncating fp32
 // accumulation chain of the tensor core at 128 steps per partial.
@@ -628,8 +687,16 @@ int64_t gemm_tc_scratch_floats(int M, int N, int K) {
 
 int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
             int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st) {
-  TcPlan pl = tc_plan(M, N, K);
   const int Np = (int)round_up(N, 4);
+  if (ep.atomic_acc) {
+    const TcPlan pa = tc_plan_atomic(M, N, K);
+    TcParams p;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.k_per_split = pa.kps; p.partial = nullptr; p.Np = Np; p.ep = ep;
+    p.out_mode = ((N & 3) == 0 && (ldc & 3) == 0 && al16(C)) ? 2 : 3;
+    return launch_tc(p, transA, b_is_nk, EPI_PLAIN, dim3(cdiv(N, BN), cdiv(M, BM), pa.splits), st);
+  }
+  TcPlan pl = tc_plan(M, N, K);
   if (pl.splits > 1 && (scratch == nullptr || scratch_floats < (int64_t)pl.splits * M * Np)) {
     pl.splits = 1;
     pl.kps = (int)round_up(K, BK);
@@ -637,6 +704,7 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
   TcParams p;
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.M = M; p.N = N; p.K = K; p.k_per_split = pl.kps; p.partial = scratch; p.Np = Np; p.ep = ep;
+  p.out_mode = pl.splits > 1 ? 1 : 0;
   dim3 grid(cdiv(N, BN), cdiv(M, BM), pl.splits);
   const int epi = pl.splits > 1 ? EPI_PLAIN : pick_epilogue(ep, C, ldc, N);
   GANFFN_TRY(launch_tc(p, transA, b_is_nk, epi, grid, st));

@@ -26,14 +26,15 @@ int attention_bwd(const float* qkv, const float* o, const float* lse, const floa
 int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T, int d, cudaStream_t st);
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
                   float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, uint64_t seed, int site,
-                  float* scratch, cudaStream_t st);
-int64_t layernorm_scratch_floats(int T, int d);
+                  cudaStream_t st);
 int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, uint64_t seed, cudaStream_t st);
 enum { EW_GELU_DROP = 0, EW_DGELU_MASK = 1, EW_DSIGMOID_MASK = 2, EW_MASK = 3 };
 int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, uint64_t seed, int site,
                 cudaStream_t st);
-int colsum(const float* a, int M, int N, float* out, int accumulate, float* scratch, cudaStream_t st);
-int64_t colsum_scratch_floats(int M, int N);
+int colsum(const float* a, int M, int N, float* out, int accumulate, cudaStream_t st);
+// dw[N,K] (+)= dy[M,N]^T x[M,K];  db[N] (+)= column sums of dy (db may be null).  accumulate = 0 zeroes first.
+int linear_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int N, int K, int accumulate,
+                 float* gemm_scratch, int64_t gemm_scratch_floats, cudaStream_t st);
 int dropout_mask(float* out, int64_t rows, int64_t cols, int64_t row_stride, float p, uint64_t seed, int site,
                  cudaStream_t st);
 

@@ -81,11 +81,7 @@ Scratch scratch_layout(const NetDims& nd) {
   mx(3 * nd.d, nd.d, Ti); mx(nd.d, nd.d, Ti); mx(nd.dff, nd.d, Ti); mx(nd.d, nd.dff, Ti);
   mx(nd.h1, nd.d, Ti); mx(nd.h2, nd.h1, Ti); mx(1, nd.h2, Ti);
   s.gemm = p; s.gemm_floats = al(g); p += s.gemm_floats;
-  int64_t r = layernorm_scratch_floats(Ti, nd.d);
-  r = std::max(r, colsum_scratch_floats(Ti, nd.dff));
-  r = std::max(r, colsum_scratch_floats(Ti, 3 * nd.d));
-  r = std::max(r, colsum_scratch_floats(Ti, std::max(nd.h1, nd.d)));
-  s.red = p; p += al(r);
+  s.red = p; p += al(32);
   s.total = p;
   return s;
 }
@@ -104,12 +100,9 @@ struct Ctx {
   int dgrad(const float* dy, const float* w, float* dx, int M, int N, int K, Epilogue ep) const {
     return gemm(dy, N, false, w, K, false, dx, K, M, K, N, ep, gemm_scratch, gemm_floats, st);
   }
-  int wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K, int accumulate) const {
-    Epilogue ep;
-    ep.beta = accumulate ? 1.f : 0.f;
-    GANFFN_TRY(gemm(dy, N, true, x, K, false, dw, K, N, K, M, ep, gemm_scratch, gemm_floats, st));
-    if (dbias) GANFFN_TRY(colsum(dy, M, N, dbias, accumulate, red, st));
-    return GANFFN_OK;
+  // gradients always accumulate into the arena (net_bwd zeroes it first when asked not to accumulate)
+  int wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K, int /*accumulate*/) const {
+    return linear_wgrad(dy, x, dw, dbias, M, N, K, 1, gemm_scratch, gemm_floats, st);
   }
 };
 
@@ -217,6 +210,20 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
   auto G = [&](int64_t o) { return grads + o; };
   const bool gen = nd.kind == GANFFN_NET_GENERATOR;
 
+  if (!accumulate) {
+    // every gradient below is accumulated (red.global.add from the GEMM / LayerNorm kernels): start from zero
+    auto Z = [&](int64_t o, int64_t n) { if (o >= 0) cudaMemsetAsync(grads + o, 0, (size_t)n * sizeof(float), st); };
+    for (int l = 0; l < nd.L; ++l) {
+      const int64_t* lo = off + (int64_t)l * PER_LAYER;
+      Z(lo[IN_W], (int64_t)3 * d * d); Z(lo[IN_B], 3 * d); Z(lo[OUT_W], (int64_t)d * d); Z(lo[OUT_B], d);
+      Z(lo[L1_W], (int64_t)nd.dff * d); Z(lo[L1_B], nd.dff); Z(lo[L2_W], (int64_t)d * nd.dff); Z(lo[L2_B], d);
+      Z(lo[N1_W], d); Z(lo[N1_B], d); Z(lo[N2_W], d); Z(lo[N2_B], d);
+    }
+    Z(hoff[FC1_W], (int64_t)nd.h1 * d); Z(hoff[FC1_B], nd.h1); Z(hoff[FC2_W], (int64_t)nd.h2 * nd.h1); Z(hoff[FC2_B], nd.h2);
+    if (!gen) { Z(hoff[FC3_W], nd.h2); Z(hoff[FC3_B], 1); }
+    if (nd.has_object()) { Z(hoff[OBJ_W], (int64_t)d * nd.d_in); Z(hoff[OBJ_B], d); }
+  }
+
   float* da = scratch + sc.da;    // gradient w.r.t. the current layer output
   float* db = scratch + sc.db;
   float* dz = scratch + sc.dz;
@@ -260,7 +267,7 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
 
     // x2 = LN2(z2), z2 = x1 + drop(linear2(h))
     GANFFN_TRY(layernorm_bwd(da, base + sl.z2, P(lo[N2_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N2_W]), G(lo[N2_B]),
-                             G(lo[L2_B]), T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 3), cx.red, st));
+                             G(lo[L2_B]), T, d, 1, p_enc, seed, GANFFN_SITE_LAYER(l, 3), st));
     GANFFN_TRY(cx.wgrad(dzd, base + sl.h, G(lo[L2_W]), nullptr, T, d, nd.dff, accumulate));
     {
       Epilogue ep; ep.dact = DACT_NONZERO; ep.dact_src = base + sl.h; ep.dact_scale = p_enc > 0.f ? 1.f / (1.f - p_enc) : 1.f;
@@ -273,7 +280,7 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
     }
     // x1 = LN1(z1), z1 = xin + drop(out_proj(o))
     GANFFN_TRY(layernorm_bwd(db, base + sl.z1, P(lo[N1_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N1_W]), G(lo[N1_B]),
-                             G(lo[OUT_B]), T, d, accumulate, p_enc, seed, GANFFN_SITE_LAYER(l, 1), cx.red, st));
+                             G(lo[OUT_B]), T, d, 1, p_enc, seed, GANFFN_SITE_LAYER(l, 1), st));
     GANFFN_TRY(cx.wgrad(dzd, base + sl.o, G(lo[OUT_W]), nullptr, T, d, d, accumulate));
     GANFFN_TRY(cx.dgrad(dzd, P(lo[OUT_W]), scratch + sc.d_o, T, d, d, Epilogue{}));
     GANFFN_TRY(attention_bwd(base + sl.qkv, base + sl.o, base + sl.lse, scratch + sc.d_o, scratch + sc.dqkv, nd.S, nd.B,

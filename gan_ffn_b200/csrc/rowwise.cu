@@ -54,12 +54,14 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // ---- LayerNorm backward -----------------------------------------------------------------------------
-// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Per-block partial dgamma/dbeta
-// go to `partial[block][2][d]`; a second kernel folds them (deterministic, no atomics).
+// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Each block folds its warps in shared memory
+// and adds its dgamma / dbeta / sublayer-bias-gradient partials to the (pre-zeroed or accumulating) outputs
+// with red.global.add: no partial buffer and no second kernel (r1 launch list: 836 fold launches per step).
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                             const float* __restrict__ gamma, float* __restrict__ dz,
-                                                            float* __restrict__ dz_drop, float* __restrict__ partial,
-                                                            int T, int d, float p_drop, uint64_t seed, uint32_t site) {
+                                                            float* __restrict__ dz_drop, float* dgamma, float* dbeta,
+                                                            float* dbias_sub, int T, int d, float p_drop, uint64_t seed,
+                                                            uint32_t site) {
   extern __shared__ __align__(16) float sm[];  // [warps][3][d]: dgamma, dbeta, colsum(dz after dropout)
   const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = d >> 2;
@@ -145,34 +147,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
+    const int seg = c / d;
+    float* out = seg == 0 ? dgamma : seg == 1 ? dbeta : dbias_sub;
+    if (out == nullptr) continue;
     float s = 0.f;
     for (int ww = 0; ww < warps; ++ww) s += sm[(size_t)ww * 3 * d + c];
-    partial[(size_t)blockIdx.x * 3 * d + c] = s;
-  }
-}
-
-// out_seg[c % seg] (+)= sum_b partial[b][c] for c in [0, n): 32 columns per block, 8 row lanes, smem fold.
-// Segment s = c / seg goes to out0/out1/out2 (a null segment pointer is skipped).
-__global__ void __launch_bounds__(256) fold_partials_kernel(const float* __restrict__ partial, int nblk, int n, int seg,
-                                                            float* out0, float* out1, float* out2, int accumulate) {
-  __shared__ float red[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (c < n)
-    for (int b = ty; b < nblk; b += 8) s += partial[(size_t)b * n + c];
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < n) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][tx];
-    const int sidx = c / seg;
-    float* base = sidx == 0 ? out0 : sidx == 1 ? out1 : out2;
-    if (base) {
-      float* dst = base + (c - sidx * seg);
-      *dst = accumulate ? *dst + t : t;
-    }
+    atomicAdd(out + (c - seg * d), s);
   }
 }
 
@@ -230,9 +210,9 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const float* __restric
 }
 
 // ---- column sums (bias gradients) ---------------------------------------------------------------------------
-// grid.x covers 32-column strips, grid.y splits the rows; partial[y][N].
+// grid.x covers 32-column strips, grid.y splits the rows; each block adds its partial with red.global.add.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a, int M, int N, int rows_per_blk,
-                                                     float* __restrict__ partial) {
+                                                     float* __restrict__ out) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -246,7 +226,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += red[k][tx];
-    partial[(size_t)blockIdx.y * N + c] = t;
+    atomicAdd(out + c, t);
   }
 }
 
@@ -273,21 +253,22 @@ int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* 
 
 static int ln_bwd_blocks(int T) { return min(cdiv(T, 8), 148 * 2); }
 
-int64_t layernorm_scratch_floats(int T, int d) { return (int64_t)ln_bwd_blocks(T) * 3 * d; }
-
 // dbias_sub (optional): column sums of the gradient that flows into the sublayer branch (dz after its
 // dropout mask) = the bias gradient of the linear layer that fed this LayerNorm's residual add.
+// accumulate = 0 zeroes dgamma / dbeta / dbias_sub first (the network path always accumulates into the arena).
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
                   float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, uint64_t seed, int site,
-                  float* scratch, cudaStream_t st) {
+                  cudaStream_t st) {
   GANFFN_CHECK_ARG(T > 0 && d > 0 && d % 4 == 0 && d <= 512, "layernorm: d=%d must be a multiple of 4 and <= 512", d);
-  GANFFN_CHECK_ARG(scratch != nullptr, "layernorm_bwd: scratch is null");
+  if (!accumulate) {
+    if (dgamma) cudaMemsetAsync(dgamma, 0, (size_t)d * sizeof(float), st);
+    if (dbeta) cudaMemsetAsync(dbeta, 0, (size_t)d * sizeof(float), st);
+    if (dbias_sub) cudaMemsetAsync(dbias_sub, 0, (size_t)d * sizeof(float), st);
+  }
   const int grid = ln_bwd_blocks(T);
-  layernorm_bwd_kernel<<<grid, 256, (size_t)8 * 3 * d * sizeof(float), st>>>(dy, z, gamma, dz, dz_drop, scratch, T, d, p,
-                                                                             seed, (uint32_t)site);
+  layernorm_bwd_kernel<<<grid, 256, (size_t)8 * 3 * d * sizeof(float), st>>>(dy, z, gamma, dz, dz_drop, dgamma, dbeta,
+                                                                             dbias_sub, T, d, p, seed, (uint32_t)site);
   GANFFN_LAUNCHED("layernorm_bwd_kernel");
-  fold_partials_kernel<<<cdiv(3 * d, 32), 256, 0, st>>>(scratch, grid, 3 * d, d, dgamma, dbeta, dbias_sub, accumulate);
-  GANFFN_LAUNCHED("fold_partials_kernel");
   return GANFFN_OK;
 }
 
@@ -318,17 +299,14 @@ static int colsum_rowblocks(int M, int N) {
   return yb < 1 ? 1 : yb;
 }
 
-int64_t colsum_scratch_floats(int M, int N) { return (int64_t)colsum_rowblocks(M, N) * N; }
-
 // out[N] (+)= column sums of a[M,N]
-int colsum(const float* a, int M, int N, float* out, int accumulate, float* scratch, cudaStream_t st) {
+int colsum(const float* a, int M, int N, float* out, int accumulate, cudaStream_t st) {
+  if (!accumulate) cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
   const int yb = colsum_rowblocks(M, N);
   const int rpb = cdiv(M, yb);
   dim3 grid(cdiv(N, 32), yb);
-  colsum_kernel<<<grid, 256, 0, st>>>(a, M, N, rpb, scratch);
+  colsum_kernel<<<grid, 256, 0, st>>>(a, M, N, rpb, out);
   GANFFN_LAUNCHED("colsum_kernel");
-  fold_partials_kernel<<<cdiv(N, 32), 256, 0, st>>>(scratch, yb, N, N, out, nullptr, nullptr, accumulate);
-  GANFFN_LAUNCHED("fold_partials_kernel");
   return GANFFN_OK;
 }
 

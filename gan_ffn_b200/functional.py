@@ -161,17 +161,14 @@ class _NetFunction(torch.autograd.Function):
         d_out = d_out.contiguous()
         ws = scratch(x.device, L.query("ganffn_net_scratch_floats", *dims))
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        accumulate = 1 if arena.grads_live() else 0
+        if not arena.grads_live():
+            # Parameter gradients are accumulated by the kernels (red.global.add from the wgrad GEMMs and the
+            # LayerNorm backward), torch-style: a fresh backward starts from a zeroed arena (one memset).
+            arena.grad.zero_()
+            arena.install_grads()
         L.call("ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
                ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
-               spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, accumulate, _stream(x))
-        if not accumulate:
-            if spec.kind == 1 and d_in == spec.d and arena.table[-1] >= 0:
-                # visual discriminator fed a D_h-wide (generated) input: `object` was bypassed
-                # (reference model.py:1355), so its gradient for this pass is zero, not stale.
-                arena.grad_views[-1].zero_()
-                arena.grad_views[-2].zero_()
-            arena.install_grads()
+               spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, 1, _stream(x))
         ctx.stash = None
         return dx, None, None, None, None, None, None, None
 

@@ -38,6 +38,7 @@ for i in range(0, len(args), 3):
         nkb = min(16, (K + 31) // 32)
         print(f"M={M} N={N} K={K} rep={rep} ({'cold' if rep == 2 else 'warm'} L2) event_us={a.elapsed_time(b)*1e3:.1f}")
         print(f"  setup_done={r(1)} prod_done={r(3)} acc_ready={r(4)} epi_done={r(5)} all_sync={r(6)}")
+        print(f"  epilogue: ld_done={r(70)} staged={r(71)} stored={r(72)} iters=" + " ".join(str(r(73+k)) for k in range(8)))
         print("  A prod arrived: " + " ".join(f"{r(8+k)}" for k in range(nkb)))
         print("  B prod arrived: " + " ".join(f"{r(24+k)}" for k in range(nkb)))
         print("  mma  (full_seen, issued):   " + " ".join(f"({r(48+2*k)},{r(49+2*k)})" for k in range(nkb)))
