@@ -179,68 +179,69 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// 16 lanes x 16 columns.  Register i of thread t lands in lane (t/4) + 8*((i>>1)&1), column 8*(i>>2) + 2*(t%4) + (i&1)
+// (probed on B200 with tools/tmem_probe.cu): a quad owns 8 consecutive bytes of a row, so a K-major operand can be
+// loaded with sector-aligned 64-bit global loads and stored without any cross-lane exchange.
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- A operand: registers -> TMEM -----------------------------------------------------------------------------
-// One thread = one row (TMEM lane) and 16 consecutive k of the K block (64 bytes of a K-major row).
-// K-major A is loaded quad-cooperatively: in load i the four lanes of a quad read the 64 contiguous bytes of row
-// 4*(lane/4)+i, so one warp instruction touches 8 rows x 2 full sectors instead of 32 rows x half a sector
-// (ncu r1: the thread-per-row pattern made the LSU/L1 miss path the limiter at ~17 B/clk/SM); a 4x4 butterfly
-// of shuffles hands every lane its own row afterwards.
+// One warp = 32 rows (its TMEM lane quadrant) x 16 k (half of a K block); 16 values per thread.
+//  K-major A ([M, lda], k contiguous): tcgen05.st.16x256b fragments.  v[8h + i] is row 16h + lane/4 + 8*((i>>1)&1),
+//    k = 8*(i>>2) + 2*(lane%4) + (i&1): eight 64-bit loads per thread, each warp instruction reads 8 rows x one
+//    full 32-byte sector.  (Thread-per-row 128-bit loads touched 32 half sectors per instruction and throttled the
+//    L1 miss path to ~17 B/clk/SM; a quad-cooperative load + shuffle transpose cost 100 extra instructions per K
+//    block in an issue-bound producer.)
+//  MN-major A ([K, lda], m contiguous): thread = row, tcgen05.st.32x32b; the warp reads 128 contiguous bytes per k.
+// `q` points at the thread's first element of this K block (see the kernel for the per-thread base pointers).
 template <bool KMAJ>
-__device__ __forceinline__ void load_a(float (&v)[16], const float* __restrict__ A, int lda, int row_base, int lane,
-                                       int M, int k0, int kend) {
-  if (KMAJ) {   // A stored [M, lda], k contiguous
-    const int g4 = lane & ~3, a = lane & 3;
+__device__ __forceinline__ void load_a(float (&v)[16], const float* __restrict__ q, int lda, int rows_left, int k_left) {
+  if (KMAJ) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int grow = row_base + g4 + i;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (grow < M && k0 + 4 * a < kend) x = __ldg(reinterpret_cast<const float4*>(A + (size_t)grow * lda + k0 + 4 * a));
-      v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-    }
-  } else {      // A stored [K, lda], m contiguous: the warp reads 128 contiguous bytes per k
-    const int grow = row_base + lane;
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int cg = 0; cg < 2; ++cg)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          float2 x = make_float2(0.f, 0.f);
+          if (16 * h + 8 * rr < rows_left && 8 * cg < k_left)
+            x = __ldg(reinterpret_cast<const float2*>(q + (size_t)(16 * h + 8 * rr) * lda + 8 * cg));
+          v[8 * h + 4 * cg + 2 * rr] = x.x;
+          v[8 * h + 4 * cg + 2 * rr + 1] = x.y;
+        }
+  } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       v[j] = 0.f;
-      if (grow < M && k0 + j < kend) v[j] = __ldg(A + (size_t)(k0 + j) * lda + grow);
+      if (rows_left > 0 && j < k_left) v[j] = __ldg(q + (size_t)j * lda);
     }
   }
 }
 
-// v[4*i + c]: chunk (lane%4) of row 4*(lane/4)+i  ->  chunk i of the lane's own row (4x4 transpose inside the quad).
-__device__ __forceinline__ void quad_transpose(float (&v)[16], int lane) {
-#pragma unroll
-  for (int b = 0; b < 2; ++b) {
-    const bool up = (lane >> b) & 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if ((i >> b) & 1) continue;
-      const int i2 = i | (1 << b);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float send = up ? v[4 * i + c] : v[4 * i2 + c];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 1 << b);
-        if (up) v[4 * i + c] = recv; else v[4 * i2 + c] = recv;
-      }
-    }
-  }
-}
-
+// hi = rna_tf32(x); lo = x - hi is exact in fp32 and handed over as is: the tensor core reads the top 19 bits of a
+// tf32 operand, i.e. truncates lo (|lo| <= 2^-11 |x|, so the truncation is <= 2^-21 |x|).
+// taddr: the warp's lane quadrant, first column of its k-half (hi); lo lives 32 columns further.
 template <bool KMAJ>
-__device__ __forceinline__ void store_a(float (&v)[16], uint32_t taddr_hi, int lane, float& rowsum) {
-  if (KMAJ) quad_transpose(v, lane);
-  rowsum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) + ((v[8] + v[9]) + (v[10] + v[11])) +
-            ((v[12] + v[13]) + (v[14] + v[15]));
+__device__ __forceinline__ void store_a(const float (&v)[16], uint32_t taddr) {
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     h[j] = tf32_rna(v[j]);
-    l[j] = tf32_rna(v[j] - __uint_as_float(h[j]));
+    l[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
   }
-  tmem_st16(taddr_hi, h);
-  tmem_st16(taddr_hi + 32, l);
+  if (KMAJ) {
+    tmem_st_16x256b_x2(taddr, h);
+    tmem_st_16x256b_x2(taddr + (16u << 16), h + 8);
+    tmem_st_16x256b_x2(taddr + 32, l);
+    tmem_st_16x256b_x2(taddr + (16u << 16) + 32, l + 8);
+  } else {
+    tmem_st16(taddr, h);
+    tmem_st16(taddr + 32, l);
+  }
   tmem_st_wait();
 }
 
@@ -248,50 +249,32 @@ __device__ __forceinline__ void store_a(float (&v)[16], uint32_t taddr_hi, int l
 // One tile = BN rows (N extent) x 32 k, 4 16-byte chunks per B-producer thread.
 constexpr int BCH = BN * 8 / NB;
 
-// KMAJ: element (n,k) at base[(row0+n)*ld + k]; else at base[k*ld + row0 + n].
+// Chunk i of a thread: K-major (element (n,k) at base[(row0+n)*ld + k]): row (tb>>3) + 32 i, k chunk tb&7;
+// MN-major (element at base[k*ld + row0 + n]): k = tb/32 + 8 i, n chunk tb%32.  Either way the global pointer of
+// chunk i is q + i*istride and its smem offset off0 + i*4096, so nothing is recomputed per K block.
 template <bool KMAJ>
-__device__ __forceinline__ void load_b(float4 (&v)[BCH], const float* __restrict__ base, int ld, int row0, int rows,
-                                       int k0, int kend, int tb) {
+__device__ __forceinline__ void load_b(float4 (&v)[BCH], const float* __restrict__ q, int64_t istride, int rows_left,
+                                       int k_left) {
 #pragma unroll
   for (int i = 0; i < BCH; ++i) {
-    const int q = tb + i * NB;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (KMAJ) {
-      const int r = q >> 3, c = q & 7;
-      const int gr = row0 + r, gk = k0 + c * 4;
-      if (gr < rows && gk < kend) v[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gr * ld + gk));
-    } else {
-      const int k = q / (BN / 4), mq = q % (BN / 4);
-      const int gk = k0 + k, gr = row0 + mq * 4;
-      if (gk < kend && gr < rows) v[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gk * ld + gr));
-    }
+    const bool ok = KMAJ ? (32 * i < rows_left && k_left > 0) : (rows_left > 0 && 8 * i < k_left);
+    if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(q + (size_t)i * istride));
   }
 }
 
-template <bool KMAJ>
-__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uint32_t lo, int tb) {
+__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uint32_t lo) {
 #pragma unroll
   for (int i = 0; i < BCH; ++i) {
-    const int q = tb + i * NB;
-    uint32_t off;
-    if (KMAJ) {
-      const int r = q >> 3, c = q & 7;
-      off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-    } else {
-      const int k = q / (BN / 4), mq = q % (BN / 4);
-      // 512-byte atoms ordered [k-group of 4][n-group of 32]: LBO = 512 B, SBO = (BN/32) * 512 B
-      off = (uint32_t)(((k >> 2) * (BN / 32) + (mq >> 3)) * 512 + (k & 3) * 128 + ((((mq & 7) >> 1) ^ (k & 3)) << 5) +
-                       ((mq & 1) << 4));
-    }
     const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       h[j] = tf32_rna(x[j]);
-      l[j] = tf32_rna(x[j] - __uint_as_float(h[j]));
+      l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));   // truncated by the tensor core (see store_a)
     }
-    sts128(hi + off, h[0], h[1], h[2], h[3]);
-    sts128(lo + off, l[0], l[1], l[2], l[3]);
+    sts128(hi + i * 4096, h[0], h[1], h[2], h[3]);
+    sts128(lo + i * 4096, l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -359,24 +342,29 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
   const bool drop = EPI == EPI_DROP && ep.p_drop > 0.0f && ep.dact == DACT_NONE;
   const bool dnz = EPI == EPI_DROP && ep.dact == DACT_NONZERO;
   const float dscale = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
-  // software pipeline: the residual / dact source / old C of row group i8+1 is in flight while i8 is computed
+  // Software pipeline (the residual / dact source / old C of row group i8+1 is in flight while i8 is computed) with
+  // strength-reduced pointers: the loop is issue-bound, 16 warps run it at once.
+  const int m_first = m_base + r0;
+  float* cptr = p.C + (size_t)m_first * p.ldc + n;
+  const float* aptr = aux_base ? aux_base + (size_t)m_first * aux_ld + n : nullptr;
+  const size_t cstep = (size_t)4 * p.ldc, astep = (size_t)4 * aux_ld;
+  uint32_t sptr = stage + (uint32_t)(r0 * 36 + cq) * 4;
+  int rows_left = p.M - m_first;                    // row i8 is valid iff 4*i8 < rows_left
+  uint64_t eidx = (uint64_t)m_first * (uint64_t)p.N + (uint64_t)n;   // dropout element index
   float4 aux_n = make_float4(0.f, 0.f, 0.f, 0.f), old_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto prefetch = [&](int i8) {
-    const int m = m_base + i8 * 4 + r0;
-    if (m < p.M) {
-      if (aux_base) aux_n = *reinterpret_cast<const float4*>(aux_base + (size_t)m * aux_ld + n);
-      if (has_beta) old_n = *reinterpret_cast<const float4*>(p.C + (size_t)m * p.ldc + n);
-    }
-  };
-  prefetch(0);
+  if (rows_left > 0) {
+    if (aptr) aux_n = *reinterpret_cast<const float4*>(aptr);
+    if (has_beta) old_n = *reinterpret_cast<const float4*>(cptr);
+  }
 #pragma unroll 1
   for (int i8 = 0; i8 < 8; ++i8) {
-    const int rr = i8 * 4 + r0, m = m_base + rr;
-    if (threadIdx.x == 0) TR(73 + i8);
+    if (rows_left <= 0) break;
     const float4 aux4 = aux_n, old4 = old_n;
-    if (i8 + 1 < 8) prefetch(i8 + 1);
-    if (m >= p.M) continue;
-    const float4 a4 = lds128(stage + (uint32_t)(rr * 36 + cq) * 4);
+    if (rows_left > 4) {
+      if (aptr) aux_n = *reinterpret_cast<const float4*>(aptr + astep);
+      if (has_beta) old_n = *reinterpret_cast<const float4*>(cptr + cstep);
+    }
+    const float4 a4 = lds128(sptr);
     float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
     const float ax[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
     if (relu) {
@@ -385,7 +373,7 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
     }
     if (drop) {
       float msk[4];
-      dropout_scale4(ep.seed, ep.site, (uint64_t)m * (uint64_t)p.N + (uint64_t)n, ep.p_drop, dscale, msk);
+      dropout_scale4(ep.seed, ep.site, eidx, ep.p_drop, dscale, msk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] *= msk[j];
     }
@@ -399,7 +387,12 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
     if (has_beta) {
       v[0] += ep.beta * old4.x; v[1] += ep.beta * old4.y; v[2] += ep.beta * old4.z; v[3] += ep.beta * old4.w;
     }
-    *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+    cptr += cstep;
+    if (aptr) aptr += astep;
+    sptr += 4 * 36 * 4;
+    rows_left -= 4;
+    eidx += (uint64_t)4 * (uint64_t)p.N;
   }
 }
 
@@ -442,8 +435,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
     const int quad = warp & 3, half = warp >> 2;
     const int row_base = m0 + quad * 32;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TM_A + half * 16);
+    // per-thread base pointer (K block 0), elements to advance per K block, remaining rows / first k of the thread
+    const float* ap = !TA ? p.A + (size_t)(row_base + (lane >> 2)) * p.lda + kbeg + half * 16 + 2 * (lane & 3)
+                          : p.A + (size_t)(kbeg + half * 16) * p.lda + row_base + lane;
+    const int64_t a_kstep = !TA ? BK : (int64_t)BK * p.lda;
+    const int a_rows_left = !TA ? p.M - (row_base + (lane >> 2)) : p.M - (row_base + lane);
+    const int a_k0 = kbeg + half * 16 + (!TA ? 2 * (lane & 3) : 0);
+    const bool want_rowsum = TA && p.ep.rowsum != nullptr && blockIdx.x == 0;   // bias gradient of a wgrad product
     float buf[RING][16];
-    float rowsum = 0.f;   // sum over this thread's k of its A row (bias gradient of a wgrad product)
+    float rowsum = 0.f;   // MN-major A: thread = row, so the row sum over k needs no exchange
     // kb0 starts at -RING: the first pass only issues the loads of K blocks 0..RING-1 (same code as steady state,
     // so nothing here is executed-once straight-line code)
     for (int kb0 = -RING; kb0 < nkb; kb0 += RING) {
@@ -455,19 +455,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
           const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
           mbar_wait(smem_u32(empty + s), ph ^ 1u);
           tc_fence_after();
-          store_a<!TA>(buf[r], trow + (uint32_t)(s * 64), lane, rowsum);
+          if (want_rowsum) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rowsum += buf[r][j];
+          }
+          store_a<!TA>(buf[r], trow + (uint32_t)(s * 64));
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full + s));
           if (t == 0 && kb < 16) TR(8 + kb);
         }
-        if (kb + RING < nkb) load_a<!TA>(buf[r], p.A, p.lda, row_base, lane, p.M, kbeg + (kb + RING) * BK + half * 16, kend);
+        const int kn = kb + RING;
+        if (kn < nkb) load_a<!TA>(buf[r], ap + kn * a_kstep, p.lda, a_rows_left, kend - (a_k0 + kn * BK));
       }
     }
-    if (p.ep.rowsum != nullptr && blockIdx.x == 0 && row_base + lane < p.M) atomicAdd(p.ep.rowsum + row_base + lane, rowsum);
+    if (want_rowsum && row_base + lane < p.M) atomicAdd(p.ep.rowsum + row_base + lane, rowsum);
   } else if (warp < NPW) {
     // ================= B producers: global -> registers -> shared memory =================
     const int tb = t - NAW * 32;
+    const float* bp;
+    int64_t b_kstep, b_istride;
+    int b_rows_left, b_k0;
+    uint32_t b_off;
+    if (TB) {   // K-major
+      const int r = tb >> 3, c = tb & 7;
+      bp = p.B + (size_t)(n0 + r) * p.ldb + kbeg + 4 * c;
+      b_kstep = BK; b_istride = (int64_t)32 * p.ldb;
+      b_rows_left = p.N - (n0 + r); b_k0 = kbeg + 4 * c;
+      b_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    } else {    // MN-major: 512-byte atoms ordered [k-group of 4][n-group of 32]: LBO = 512 B, SBO = (BN/32) * 512 B
+      const int k = tb >> 5, mq = tb & 31;
+      bp = p.B + (size_t)(kbeg + k) * p.ldb + n0 + 4 * mq;
+      b_kstep = (int64_t)BK * p.ldb; b_istride = (int64_t)8 * p.ldb;
+      b_rows_left = p.N - (n0 + 4 * mq); b_k0 = kbeg + k;
+      b_off = (uint32_t)(((k >> 2) * (BN / 32) + (mq >> 3)) * 512 + (k & 3) * 128 + ((((mq & 7) >> 1) ^ (k & 3)) << 5) +
+                         ((mq & 1) << 4));
+    }
+    const uint32_t b_smem = smem_u32(smem) + b_off;
     float4 buf[RING][BCH];
     for (int kb0 = -RING; kb0 < nkb; kb0 += RING) {
 #pragma unroll
@@ -477,14 +501,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
           const int s = kb % STAGES;
           const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
           mbar_wait(smem_u32(empty + s), ph ^ 1u);
-          const uint32_t st = smem_u32(smem) + (uint32_t)(s * STAGE);
-          store_b<TB>(buf[r], st, st + B_TILE, tb);
+          const uint32_t st = b_smem + (uint32_t)(s * STAGE);
+          store_b(buf[r], st, st + B_TILE);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full + s));
           if (tb == 0 && kb < 16) TR(24 + kb);
         }
-        if (kb + RING < nkb) load_b<TB>(buf[r], p.B, p.ldb, n0, p.N, kbeg + (kb + RING) * BK, kend, tb);
+        const int kn = kb + RING;
+        if (kn < nkb) load_b<TB>(buf[r], bp + kn * b_kstep, b_istride, b_rows_left, kend - (b_k0 + kn * BK));
       }
     }
   } else {
@@ -687,6 +712,7 @@ int64_t gemm_tc_scratch_floats(int M, int N, int K) {
 
 int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool b_is_nk, float* C, int ldc, int M, int N,
             int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st) {
+  GANFFN_CHECK_ARG(ep.rowsum == nullptr || transA, "gemm_tc: rowsum needs an MN-major (transposed) A operand");
   const int Np = (int)round_up(N, 4);
   if (ep.atomic_acc) {
     const TcPlan pa = tc_plan_atomic(M, N, K);
