@@ -140,7 +140,7 @@ template <int HD>
 __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_fwd_kernel(const float* __restrict__ qkv,
                                                                          float* __restrict__ o, float* __restrict__ lse,
                                                                          int S, int B, int d, int nhead, float p_drop,
-                                                                         uint64_t seed, uint32_t site) {
+                                                                         const Seed seed_ref, uint32_t site) {
   extern __shared__ __align__(16) float smem[];
   const int SP = S | 1;
   float* Qs = smem;              // [S][HD]
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_fwd_kernel(const f
   mx = fmaxf(fmaxf(red[ir], red[S + ir]), fmaxf(red[2 * S + ir], red[3 * S + ir]));
   __syncthreads();
   const bool drop = p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int S4 = (S + 3) & ~3;
   const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
@@ -226,7 +227,7 @@ template <int HD>
 __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
     const float* __restrict__ d_o, float* __restrict__ dqkv, int S, int B, int d, int nhead, float p_drop,
-    uint64_t seed, uint32_t site) {
+    const Seed seed_ref, uint32_t site) {
   extern __shared__ __align__(16) float smem[];
   const int SP = S | 1;  // odd row stride for the S x S matrices
   float* Qs = smem;                 // [S][HD]
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
   const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
   const float scale = rsqrtf((float)HD);
   const bool drop = p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int S4 = (S + 3) & ~3;
   const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
 inline int att_threads(int S) { return NG * ((S + 31) / 32) * 32; }
 
 template <int HD>
-int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, uint64_t seed, int site,
+int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed, int site,
                cudaStream_t st) {
   auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)s * (s | 1) + (size_t)NG * s) * sizeof(float); };
   static bool attr_done = false;
@@ -326,7 +328,7 @@ int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int 
 
 template <int HD>
 int launch_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
-               int nhead, float p, uint64_t seed, int site, cudaStream_t st) {
+               int nhead, float p, Seed seed, int site, cudaStream_t st) {
   auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s * (s | 1) + s) * sizeof(float); };
   static bool attr_done = false;
   if (!attr_done) {
@@ -342,7 +344,7 @@ int launch_bwd(const float* qkv, const float* o, const float* lse, const float* 
 
 }  // namespace
 
-int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, uint64_t seed,
+int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed,
                   int site, cudaStream_t st) {
   GANFFN_CHECK_ARG(S >= 1 && S <= GANFFN_MAX_SEQ, "attention: seq_len %d outside [1,%d] (model.py:1179)", S,
                    GANFFN_MAX_SEQ);
@@ -360,7 +362,7 @@ int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, i
 }
 
 int attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
-                  int nhead, float p, uint64_t seed, int site, cudaStream_t st) {
+                  int nhead, float p, Seed seed, int site, cudaStream_t st) {
   GANFFN_CHECK_ARG(S >= 1 && S <= GANFFN_MAX_SEQ, "attention: seq_len %d outside [1,%d] (model.py:1179)", S,
                    GANFFN_MAX_SEQ);
   GANFFN_CHECK_ARG(B >= 1 && nhead >= 1 && d % nhead == 0, "attention: d=%d not divisible by nhead=%d", d, nhead);

@@ -243,6 +243,12 @@ int ganffn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, in
   return adam_step(p, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale, S(stream));
 }
 
+int ganffn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  GANFFN_CHECK_ARG(p && g && m && v && step_dev, "adam_step_dev: null pointer");
+  return adam_step_dev(p, g, m, v, n, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale, S(stream));
+}
+
 static NetDims dims(int kind, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1, int h2) {
   NetDims nd;
   nd.kind = kind; nd.S = S_; nd.B = B; nd.d_in = d_in; nd.d = d; nd.nhead = nhead; nd.dff = dff; nd.L = nlayers;
@@ -252,17 +258,17 @@ static NetDims dims(int kind, int S_, int B, int d_in, int d, int nhead, int dff
 
 int ganffn_net_fwd(int kind, const float* params, const int64_t* off, const float* pe, const float* x, float* out,
                    float* stash, float* scratch, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1,
-                   int h2, int train, float p_head, uint64_t seed, void* stream) {
+                   int h2, int train, float p_head, uint64_t seed, const uint64_t* seed_dev, void* stream) {
   return net_fwd(dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2), params, off, pe, x, out, stash, scratch, train,
-                 p_head, seed, S(stream));
+                 p_head, Seed(seed, seed_dev), S(stream));
 }
 
 int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const float* x, const float* out,
                    const float* d_out_grad, const float* stash, float* grads, float* dx, float* scratch, int S_, int B,
                    int d_in, int d, int nhead, int dff, int nlayers, int h1, int h2, int train, float p_head,
-                   uint64_t seed, int accumulate, void* stream) {
+                   uint64_t seed, const uint64_t* seed_dev, int accumulate, void* stream) {
   return net_bwd(dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2), params, off, x, out, d_out_grad, stash, grads,
-                 dx, scratch, train, p_head, seed, accumulate, S(stream));
+                 dx, scratch, train, p_head, Seed(seed, seed_dev), accumulate, S(stream));
 }
 
 int64_t ganffn_net_stash_floats(int kind, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1,

@@ -43,6 +43,16 @@ void set_error(const char* fmt, ...);
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// ---- dropout seed: an immediate, or (CUDA-graph safe) a device word that a replayed graph re-reads ------------
+struct Seed {
+  uint64_t v = 0;
+  const uint64_t* p = nullptr;
+  Seed() = default;
+  Seed(uint64_t value) : v(value), p(nullptr) {}   // NOLINT: implicit on purpose (C ABI passes plain integers)
+  Seed(uint64_t value, const uint64_t* ptr) : v(value), p(ptr) {}
+};
+__device__ __forceinline__ uint64_t seed_value(const Seed& s) { return s.p ? __ldg(reinterpret_cast<const unsigned long long*>(s.p)) : s.v; }
+
 // ---- Philox4x32-10 -----------------------------------------------------------------------
 // counter = (group_lo, group_hi, site, 0), key = (seed_lo, seed_hi).  One call yields the four
 // uniforms of elements 4*group .. 4*group+3 of a dropout site.
@@ -128,7 +138,7 @@ struct Epilogue {
   int act = GANFFN_ACT_NONE;
   int drop_before_act = 0;
   float p_drop = 0.0f;              // forward dropout (or backward mask regeneration for dact)
-  uint64_t seed = 0;
+  Seed seed;
   uint32_t site = 0;
   // backward-through-activation: v *= f(dact_src[m,n])
   int dact = DACT_NONE;
@@ -155,7 +165,7 @@ __device__ __forceinline__ void epilogue_store4(const Epilogue& ep, float* C, in
   }
   const bool drop = ep.p_drop > 0.0f;
   float msk[4] = {1.f, 1.f, 1.f, 1.f};
-  if (drop) dropout_scale4(ep.seed, ep.site, (uint64_t)m * (uint64_t)N + (uint64_t)n, ep.p_drop, 1.0f / (1.0f - ep.p_drop), msk);
+  if (drop) dropout_scale4(seed_value(ep.seed), ep.site, (uint64_t)m * (uint64_t)N + (uint64_t)n, ep.p_drop, 1.0f / (1.0f - ep.p_drop), msk);
   if (ep.dact == DACT_NONE) {
     if (drop && ep.drop_before_act) {
 #pragma unroll

@@ -342,6 +342,7 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
   const bool drop = EPI == EPI_DROP && ep.p_drop > 0.0f && ep.dact == DACT_NONE;
   const bool dnz = EPI == EPI_DROP && ep.dact == DACT_NONZERO;
   const float dscale = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
+  const uint64_t seedv = drop ? seed_value(ep.seed) : 0ull;
   // Software pipeline (the residual / dact source / old C of row group i8+1 is in flight while i8 is computed) with
   // strength-reduced pointers: the loop is issue-bound, 16 warps run it at once.
   const int m_first = m_base + r0;
@@ -373,7 +374,7 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
     }
     if (drop) {
       float msk[4];
-      dropout_scale4(ep.seed, ep.site, eidx, ep.p_drop, dscale, msk);
+      dropout_scale4(seedv, ep.site, eidx, ep.p_drop, dscale, msk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] *= msk[j];
     }

@@ -17,19 +17,19 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
 int64_t gemm_tc_scratch_floats(int M, int N, int K);
 
 // attention.cu
-int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, uint64_t seed,
+int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed,
                   int site, cudaStream_t st);
 int attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
-                  int nhead, float p, uint64_t seed, int site, cudaStream_t st);
+                  int nhead, float p, Seed seed, int site, cudaStream_t st);
 
 // rowwise.cu
 int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T, int d, cudaStream_t st);
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
-                  float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, uint64_t seed, int site,
+                  float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, Seed seed, int site,
                   cudaStream_t st);
-int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, uint64_t seed, cudaStream_t st);
+int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, Seed seed, cudaStream_t st);
 enum { EW_GELU_DROP = 0, EW_DGELU_MASK = 1, EW_DSIGMOID_MASK = 2, EW_MASK = 3 };
-int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, uint64_t seed, int site,
+int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, Seed seed, int site,
                 cudaStream_t st);
 int colsum(const float* a, int M, int N, float* out, int accumulate, cudaStream_t st);
 // dw[N,K] (+)= dy[M,N]^T x[M,K];  db[N] (+)= column sums of dy (db may be null).  accumulate = 0 zeroes first.
@@ -51,6 +51,8 @@ int masked_nll_bwd(const float* d_loss, const float* loss_and_den, const int64_t
 int bce_fwd(const float* prob, const float* target, float* loss, int64_t n, float scale, cudaStream_t st);
 int bce_bwd(const float* d_loss, const float* prob, const float* target, float* d_prob, int64_t n, float scale,
             cudaStream_t st);
+int adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, float lr, float b1,
+                  float b2, float eps, float wd, float gscale, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2, float eps,
               float wd, float gscale, cudaStream_t st);
 
@@ -61,10 +63,10 @@ struct NetDims {
   bool has_object() const { return d_in != d; }
 };
 int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const float* pe, const float* x, float* out,
-            float* stash, float* scratch, int train, float p_head, uint64_t seed, cudaStream_t st);
+            float* stash, float* scratch, int train, float p_head, Seed seed, cudaStream_t st);
 int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const float* x, const float* out,
             const float* d_out, const float* stash, float* grads, float* dx, float* scratch, int train, float p_head,
-            uint64_t seed, int accumulate, cudaStream_t st);
+            Seed seed, int accumulate, cudaStream_t st);
 int64_t net_stash_floats(const NetDims& nd);
 int64_t net_scratch_floats(const NetDims& nd);
 int net_check(const NetDims& nd);

@@ -223,10 +223,17 @@ __global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ 
 }
 
 // ---- Adam over a flat arena: 28 B/param of HBM traffic, float4 ---------------------------------------------
+// step_dev == nullptr: lr_bc1 / inv_sqrt_bc2 are the host-computed bias corrections.  Otherwise lr_bc1 carries the
+// plain learning rate and the corrections are derived here from the device-resident step count (graph replay).
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_bc1,
                                                    float inv_sqrt_bc2, float b1, float b2, float eps, float wd,
-                                                   float gscale) {
+                                                   float gscale, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const double step = (double)__ldg(step_dev);
+    lr_bc1 = (float)((double)lr_bc1 / (1.0 - pow((double)b1, step)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, step)));
+  }
   const int64_t nvec = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -327,7 +334,18 @@ int adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,
   const double bc2 = 1.0 - pow((double)b2, (double)step);
   const int grid = (int)std::min<int64_t>(cdiv((n >> 2) + 1, 256), 148 * 8);
   adam_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps, wd,
-                                    gscale);
+                                    gscale, nullptr);
+  GANFFN_LAUNCHED("adam_kernel");
+  return GANFFN_OK;
+}
+
+int adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, float lr, float b1,
+                  float b2, float eps, float wd, float gscale, cudaStream_t st) {
+  GANFFN_CHECK_ARG(n > 0, "adam: n=%lld", (long long)n);
+  GANFFN_CHECK_ARG(((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0,
+                   "adam: arenas must be 16-byte aligned");
+  const int grid = (int)std::min<int64_t>(cdiv((n >> 2) + 1, 256), 148 * 8);
+  adam_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, 1.0f, b1, b2, eps, wd, gscale, step_dev);
   GANFFN_LAUNCHED("adam_kernel");
   return GANFFN_OK;
 }

@@ -127,7 +127,7 @@ int64_t net_stash_floats(const NetDims& nd) { return stash_layout(nd).total; }
 int64_t net_scratch_floats(const NetDims& nd) { return scratch_layout(nd).total; }
 
 int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const float* pe, const float* x, float* out,
-            float* stash, float* scratch, int train, float p_head, uint64_t seed, cudaStream_t st) {
+            float* stash, float* scratch, int train, float p_head, Seed seed, cudaStream_t st) {
   GANFFN_TRY(net_check(nd));
   GANFFN_CHECK_ARG(params && off && pe && x && out && stash && scratch, "net_fwd: null pointer");
   const Stash sl = stash_layout(nd);
@@ -197,7 +197,7 @@ int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const fl
 
 int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const float* x, const float* out,
             const float* d_out, const float* stash, float* grads, float* dx, float* scratch, int train, float p_head,
-            uint64_t seed, int accumulate, cudaStream_t st) {
+            Seed seed, int accumulate, cudaStream_t st) {
   GANFFN_TRY(net_check(nd));
   GANFFN_CHECK_ARG(params && off && x && out && d_out && stash && grads && scratch, "net_bwd: null pointer");
   const Stash sl = stash_layout(nd);

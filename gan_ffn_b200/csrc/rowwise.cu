@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                             const float* __restrict__ gamma, float* __restrict__ dz,
                                                             float* __restrict__ dz_drop, float* dgamma, float* dbeta,
-                                                            float* dbias_sub, int T, int d, float p_drop, uint64_t seed,
+                                                            float* dbias_sub, int T, int d, float p_drop, const Seed seed_ref,
                                                             uint32_t site) {
   extern __shared__ __align__(16) float sm[];  // [warps][3][d]: dgamma, dbeta, colsum(dz after dropout)
   const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     gm[k] = c < nv ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const bool drop = (dz_drop != nullptr) && p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
 
   for (int row = blockIdx.x * warps + w; row < T; row += gridDim.x * warps) {
@@ -159,8 +160,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // ---- positional encoding ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) posenc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pe,
                                                          float* __restrict__ y, int64_t nvec, int B, int d, float p_drop,
-                                                         uint64_t seed) {
+                                                         const Seed seed_ref) {
   const bool drop = p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int dv = d >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -186,8 +188,9 @@ __global__ void __launch_bounds__(256) posenc_fwd_kernel(const float* __restrict
 // mode 3: y = dy * mask                                      (backward through dropout only)
 __global__ void __launch_bounds__(256) elementwise_kernel(const float* __restrict__ a, const float* __restrict__ src,
                                                           float* __restrict__ y, int64_t n, int mode, float p_drop,
-                                                          uint64_t seed, uint32_t site) {
+                                                          const Seed seed_ref, uint32_t site) {
   const bool drop = p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int64_t nvec = (n + 3) >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -257,7 +260,7 @@ static int ln_bwd_blocks(int T) { return min(cdiv(T, 8), 148 * 2); }
 // dropout mask) = the bias gradient of the linear layer that fed this LayerNorm's residual add.
 // accumulate = 0 zeroes dgamma / dbeta / dbias_sub first (the network path always accumulates into the arena).
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
-                  float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, uint64_t seed, int site,
+                  float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, Seed seed, int site,
                   cudaStream_t st) {
   GANFFN_CHECK_ARG(T > 0 && d > 0 && d % 4 == 0 && d <= 512, "layernorm: d=%d must be a multiple of 4 and <= 512", d);
   if (!accumulate) {
@@ -272,7 +275,7 @@ int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz
   return GANFFN_OK;
 }
 
-int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, uint64_t seed, cudaStream_t st) {
+int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, Seed seed, cudaStream_t st) {
   GANFFN_CHECK_ARG(S >= 1 && S <= GANFFN_MAX_SEQ, "posenc: seq_len %d outside [1,%d] (model.py:1179)", S, GANFFN_MAX_SEQ);
   GANFFN_CHECK_ARG(d % 4 == 0, "posenc: d=%d must be a multiple of 4", d);
   const int64_t nvec = (int64_t)S * B * (d / 4);
@@ -282,7 +285,7 @@ int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, f
   return GANFFN_OK;
 }
 
-int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, uint64_t seed, int site,
+int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, Seed seed, int site,
                 cudaStream_t st) {
   if (n <= 0) return GANFFN_OK;
   const int grid = (int)std::min<int64_t>(cdiv((n + 3) / 4, 256), 148 * 8);

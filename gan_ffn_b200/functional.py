@@ -35,6 +35,64 @@ def next_seed() -> int:
     return x
 
 
+class DeviceSeedStream:
+    """Graph-safe dropout seeds.  ``slots`` is a device int64 vector that ``advance()`` refills *on the device* from
+    (base, step counter) with a splitmix64-style hash, using only torch ops, so the refill can be captured into a
+    CUDA graph: every replay draws fresh masks although the kernels' arguments are frozen.  Each network forward of
+    a step takes the next slot (``take()``) and hands its address to the kernels (``seed_dev`` of ganffn_net_fwd);
+    the backward pass of that call re-reads the same word."""
+
+    _K = [0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB, 0xD1B54A32D192ED03]
+
+    @staticmethod
+    def _s64(x: int) -> int:
+        x &= _MASK64
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def __init__(self, device, n_slots: int = 64, base: Optional[int] = None):
+        self.device = torch.device(device)
+        self.n = n_slots
+        base = int(torch.initial_seed()) if base is None else int(base)
+        self.base = torch.tensor([self._s64(base * self._K[3])], dtype=torch.int64, device=self.device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.idx = torch.arange(1, n_slots + 1, dtype=torch.int64, device=self.device) * self._s64(self._K[0])
+        self.slots = torch.zeros(n_slots, dtype=torch.int64, device=self.device)
+        self.next = 0
+        self.advance()
+
+    def advance(self) -> None:
+        """Start of a step: new seeds for all slots (device-side; capturable)."""
+        self.counter.add_(1)
+        z = self.base + self.counter * self._s64(self._K[2]) + self.idx
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * self._s64(self._K[1])
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * self._s64(self._K[2])
+        z = z ^ ((z >> 31) & ((1 << 33) - 1))
+        self.slots.copy_(z)
+        self.next = 0
+
+    def take(self) -> int:
+        """Device address of the next seed word of this step."""
+        if self.next >= self.n:
+            raise RuntimeError(f"DeviceSeedStream: more than {self.n} dropout-drawing forward calls in one step")
+        p = self.slots.data_ptr() + 8 * self.next
+        self.next += 1
+        return p
+
+    def value(self, slot: int) -> int:
+        """Host copy of a slot as the unsigned 64-bit seed the kernels see (tests)."""
+        return int(self.slots[slot].item()) & _MASK64
+
+
+_seed_stream: Optional[DeviceSeedStream] = None
+
+
+def set_seed_stream(stream: Optional[DeviceSeedStream]) -> Optional[DeviceSeedStream]:
+    """Route the dropout seeds of all train-mode forwards through a DeviceSeedStream (None = host seeds)."""
+    global _seed_stream
+    prev, _seed_stream = _seed_stream, stream
+    return prev
+
+
 # --------------------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------------------
@@ -135,7 +193,7 @@ class _NetFunction(torch.autograd.Function):
     only autograd edge is the input ``x``."""
 
     @staticmethod
-    def forward(ctx, x, anchor, arena: ParamArena, spec: NetSpec, pe, train: bool, p_head: float, seed: int):
+    def forward(ctx, x, anchor, arena: ParamArena, spec: NetSpec, pe, train: bool, p_head: float, seed: int, seed_ptr):
         L = lib()
         S, B, d_in = x.shape
         dims = spec.dims(S, B, d_in)
@@ -146,8 +204,8 @@ class _NetFunction(torch.autograd.Function):
         out = torch.empty((S, B, spec.h2 if spec.kind == 0 else 1), dtype=torch.float32, device=x.device)
         L.call("ganffn_net_fwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(pe), ptr(x), ptr(out),
                ptr(stash), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff, spec.nlayers, spec.h1, spec.h2,
-               int(train), float(p_head), seed, _stream(x))
-        ctx.arena, ctx.spec, ctx.train, ctx.p_head, ctx.seed = arena, spec, train, p_head, seed
+               int(train), float(p_head), seed, seed_ptr, _stream(x))
+        ctx.arena, ctx.spec, ctx.train, ctx.p_head, ctx.seed, ctx.seed_ptr = arena, spec, train, p_head, seed, seed_ptr
         ctx.stash = stash
         ctx.save_for_backward(x, out)
         return out
@@ -168,9 +226,9 @@ class _NetFunction(torch.autograd.Function):
             arena.install_grads()
         L.call("ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
                ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
-               spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, 1, _stream(x))
+               spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, ctx.seed_ptr, 1, _stream(x))
         ctx.stash = None
-        return dx, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None
 
 
 def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Tensor, train: bool, p_head: float):
@@ -178,11 +236,16 @@ def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Ten
     if x.dim() != 3:
         raise ValueError(f"expected (seq_len, batch, dim) input, got shape {tuple(x.shape)}")
     x = x.contiguous()
-    seed = next_seed() if train else 0
+    seed, seed_ptr = 0, None
+    if train:
+        if _seed_stream is not None:
+            seed_ptr = _seed_stream.take()
+        else:
+            seed = next_seed()
     anchor = arena.flat
     if arena.requires_grad and torch.is_grad_enabled():
         anchor = arena.flat.detach().requires_grad_(True)  # makes autograd call backward even for data inputs
-    return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed)
+    return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr)
 
 
 # --------------------------------------------------------------------------------------

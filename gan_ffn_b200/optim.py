@@ -68,6 +68,19 @@ class FusedAdam:
                 elif p.grad is not None:
                     p.grad.zero_()
 
+    def _state_for(self, key, like: torch.Tensor):
+        """Adam state of an arena / loose parameter.  The step count lives on the device (``step_t``) and is bumped by
+        a captured torch op, so ``step()`` can be recorded into a CUDA graph and replayed (bias correction is
+        derived in the kernel from ``*step_t``); ``step`` mirrors it on the host for eager use."""
+        st = self.state.get(id(key))
+        if st is None:
+            st = {"step": 0, "m": torch.zeros_like(like), "v": torch.zeros_like(like), "keep": key,
+                  "step_t": torch.zeros(1, dtype=torch.int32, device=like.device)}
+            self.state[id(key)] = st
+        st["step"] += 1
+        st["step_t"].add_(1)
+        return st
+
     @torch.no_grad()
     def step(self):
         L = lib()
@@ -79,19 +92,11 @@ class FusedAdam:
         if self.grad_reducer is not None:
             self.grad_reducer.reduce([ar.grad for ar in live] + [p.grad for p in loose])
         for ar in live:
-            st = self.state.get(id(ar))
-            if st is None:
-                st = {"step": 0, "m": torch.zeros_like(ar.flat), "v": torch.zeros_like(ar.flat), "keep": ar}
-                self.state[id(ar)] = st
-            st["step"] += 1
-            L.call("ganffn_adam_step", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel, st["step"],
-                   lr, b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(ar.flat))
+            st = self._state_for(ar, ar.flat)
+            L.call("ganffn_adam_step_dev", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel,
+                   ptr(st["step_t"]), lr, b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(ar.flat))
         for p in loose:
-            st = self.state.get(id(p))
-            if st is None:
-                st = {"step": 0, "m": torch.zeros_like(p), "v": torch.zeros_like(p), "keep": p}
-                self.state[id(p)] = st
-            st["step"] += 1
+            st = self._state_for(p, p)
             g = p.grad.contiguous()
-            L.call("ganffn_adam_step", ptr(p), ptr(g), ptr(st["m"]), ptr(st["v"]), p.numel(), st["step"], lr, b1, b2,
-                   self.eps, self.weight_decay, self.grad_scale, GF._stream(p))
+            L.call("ganffn_adam_step_dev", ptr(p), ptr(g), ptr(st["m"]), ptr(st["v"]), p.numel(), ptr(st["step_t"]), lr,
+                   b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(p))

@@ -138,6 +138,74 @@ class ClassifierTrainer:
         return loss.detach(), pred_, labels_
 
 
+class GraphedTrainStep:
+    """One train step (stage-1 GAN batch and/or stage-2 classifier step) as a replayed CUDA graph
+    (the twelve sub-steps are ~5000 kernel launches; replay removes their launch overhead).
+
+    The loop bodies are the same Python as the eager path -- they are simply *recorded* once per batch shape:
+    the first call for a shape runs eagerly (it is a real training step and doubles as warm-up), the second call
+    captures, every later call copies the batch into the graph's static input tensors and replays.  What makes the
+    recording replayable: dropout seeds come from a ``DeviceSeedStream`` that the graph advances on the device, the
+    Adam step count lives on the device, and the kernels never allocate or synchronise.
+
+    Returns a dict of device tensors owned by the graph (read them before the next call): the six GAN losses and,
+    with a classifier, ``loss`` / ``pred`` / ``labels``."""
+
+    def __init__(self, gan: "GANTrainer" = None, cls: "ClassifierTrainer" = None, seed=None, enabled: bool = True):
+        if gan is None and cls is None:
+            raise ValueError("GraphedTrainStep needs a GANTrainer and/or a ClassifierTrainer")
+        self.gan, self.cls, self.enabled = gan, cls, enabled
+        self.seed = seed
+        self.seeds = None
+        self._seen, self._graphs = set(), {}
+        self.kernels_per_replay = {}   # shape key -> kernels of this library recorded in the graph
+        self.last_key = None
+        if (gan is not None and gan.grad_reducer is not None) or (cls is not None and cls.grad_reducer is not None):
+            self.enabled = False   # the data-parallel collectives read host scalars per step; run those eagerly
+
+    def _body(self, batch: Batch):
+        out = {}
+        if self.gan is not None:
+            out.update(self.gan.batch(batch))
+        if self.cls is not None:
+            loss, pred, labels = self.cls.step(batch, train=True)
+            out.update(loss=loss, pred=pred, labels=labels)
+        return out
+
+    def __call__(self, batch: Batch):
+        from . import functional as GF
+        dev = batch.text.device
+        if self.seeds is None:
+            self.seeds = GF.DeviceSeedStream(dev, base=self.seed)
+        prev = GF.set_seed_stream(self.seeds)
+        try:
+            key = (tuple(batch.text.shape), tuple(batch.visual.shape), dev.index)
+            self.last_key = key
+            if not self.enabled or key not in self._seen:
+                self._seen.add(key)
+                self.seeds.advance()
+                return self._body(batch)
+            if key not in self._graphs:
+                static = Batch(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in vars(batch).items()})
+                torch.cuda.synchronize(dev)
+                from ._lib import lib
+                n0 = int(lib().cdll.ganffn_launch_count())
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.seeds.advance()
+                    out = self._body(static)
+                self.kernels_per_replay[key] = int(lib().cdll.ganffn_launch_count()) - n0
+                self._graphs[key] = (graph, static, out)
+            graph, static, out = self._graphs[key]
+            for k, v in vars(batch).items():
+                if torch.is_tensor(v):
+                    getattr(static, k).copy_(v, non_blocking=True)
+            graph.replay()
+            return out
+        finally:
+            GF.set_seed_stream(prev)
+
+
 def build_networks(D_h: int = 100, n_classes: int = 6, device="cuda", seed: int = 3407):
     """The six networks + GAN_FFN as the reference's ``__main__`` builds them
     (train_IEMOCAP.py:580-585, :629-635: GAN dropout 0.2, GAN_FFN dropout --dropout 0.6)."""

@@ -164,6 +164,10 @@ int ganffn_bce_bwd(const float* d_loss, const float* prob, const float* target, 
 int ganffn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr,
                      float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                      void* stream);
+/* Same, with the step count read from device memory (`*step_dev`, >= 1) so that the call can be captured in a CUDA
+ * graph; the caller increments the counter on the same stream before the call. */
+int ganffn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 /* ---- whole networks -------------------------------------------------------------------- */
 /* One generator / discriminator forward: [object] -> PE -> nlayers x encoder layer -> head.
@@ -184,18 +188,20 @@ int ganffn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, in
  *   scratch     ganffn_net_scratch_floats() floats of workspace (split-K partials etc.).
  *   p_scale     0 = eval mode (all dropout off); 1 = train mode (reference probabilities:
  *               PE 0.2, encoder 0.1, head `p_head`).
+ *   seed        dropout seed of this forward call; when `seed_dev` is not NULL the kernels read the seed from
+ *               that device word instead, so a captured CUDA graph draws fresh masks on every replay.
  * Replaces model.py:1221-1231, 1255-1263, 1286-1294, 1320-1327, 1354-1364, 1390-1397. */
 int ganffn_net_fwd(int kind, const float* params, const int64_t* off, const float* pe,
                    const float* x, float* out, float* stash, float* scratch, int S, int B, int d_in,
                    int d, int nhead, int dff, int nlayers, int h1, int h2, int train, float p_head,
-                   uint64_t seed, void* stream);
+                   uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* Backward of the above.  grads has the arena's layout; accumulate != 0 adds into it.
  * dx may be NULL when the input needs no gradient.  scratch: ganffn_net_scratch_floats(). */
 int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const float* x,
                    const float* out, const float* d_out_grad, const float* stash, float* grads,
                    float* dx, float* scratch, int S, int B, int d_in, int d, int nhead, int dff,
                    int nlayers, int h1, int h2, int train, float p_head, uint64_t seed,
-                   int accumulate, void* stream);
+                   const uint64_t* seed_dev, int accumulate, void* stream);
 /* Both return -1 when the shape violates a precondition (ganffn_last_error() says which). */
 int64_t ganffn_net_stash_floats(int kind, int S, int B, int d_in, int d, int nhead, int dff,
                                 int nlayers, int h1, int h2);
