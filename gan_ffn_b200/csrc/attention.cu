@@ -310,11 +310,295 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
   if (active) store_cols<HD>(out + d, c0, acc, 1.f);
 }
 
+
+// ================================================================================================================
+// Small head_dim (<= 16: the five d=100 networks, head_dim 10).  Same decomposition -- lane = query row, four warp
+// groups split the keys -- but the probabilities never leave the registers of the thread that computed them: each
+// group accumulates P V (and dQ in the backward pass) over its own quarter of the keys and the four partial rows
+// are folded through shared memory.  ncu on the first version (S x S matrix in smem, column-split P V sweeps): 11.7 M
+// warp instructions forward / 23.8 M backward per d=100 layer at S=94 B=32, issue-bound at ~50 % issue utilisation
+// with two CTAs per SM; this version executes about half of that and needs no S x S matrix in the forward pass.
+// ================================================================================================================
+template <int HD>
+__device__ __forceinline__ void axpy_row(float a, const float* __restrict__ row, float* acc) {
+  constexpr int W = Cfg<HD>::W;
+  if (W == 4) {
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(row + 4 * c);
+      acc[4 * c] = fmaf(a, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(a, v.y, acc[4 * c + 1]);
+      acc[4 * c + 2] = fmaf(a, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(a, v.w, acc[4 * c + 3]);
+    }
+  } else if (W == 2) {
+#pragma unroll
+    for (int c = 0; c < HD / 2; ++c) {
+      const float2 v = *reinterpret_cast<const float2*>(row + 2 * c);
+      acc[2 * c] = fmaf(a, v.x, acc[2 * c]); acc[2 * c + 1] = fmaf(a, v.y, acc[2 * c + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = fmaf(a, row[c], acc[c]);
+  }
+}
+
+// row of HD floats in global memory (8-byte aligned when HD is even, 16-byte when HD % 4 == 0)
+template <int HD>
+__device__ __forceinline__ void store_row(float* g, const float* acc, float mul) {
+  constexpr int W = Cfg<HD>::W;
+  if (W == 4) {
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c)
+      *reinterpret_cast<float4*>(g + 4 * c) = make_float4(acc[4 * c] * mul, acc[4 * c + 1] * mul, acc[4 * c + 2] * mul, acc[4 * c + 3] * mul);
+  } else if (W == 2) {
+#pragma unroll
+    for (int c = 0; c < HD / 2; ++c) *reinterpret_cast<float2*>(g + 2 * c) = make_float2(acc[2 * c] * mul, acc[2 * c + 1] * mul);
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; ++c) g[c] = acc[c] * mul;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_fwd_small_kernel(const float* __restrict__ qkv,
+                                                                               float* __restrict__ o, float* __restrict__ lse,
+                                                                               int S, int B, int d, int nhead, float p_drop,
+                                                                               const Seed seed_ref, uint32_t site) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PW = HD | 1;         // odd row stride of the partial rows (lane = row: conflict-free)
+  float* Qs = smem;                  // [S][HD]
+  float* Ks = Qs + S * HD;
+  float* Vs = Ks + S * HD;
+  float* redm = Vs + S * HD;         // [NG][S] partial row max
+  float* reds = redm + NG * S;       // [NG][S] partial row sums
+  float* part = reds + NG * S;       // [NG-1][S][PW] partial P V rows of groups 1..NG-1
+  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  const int ld = B * 3 * d;
+  const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
+  load_tile<HD>(base, ld, Qs, S);
+  load_tile<HD>(base + d, ld, Ks, S);
+  load_tile<HD>(base + 2 * d, ld, Vs, S);
+  __syncthreads();
+
+  const int nrw = (S + 31) >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = warp / nrw, i = (warp % nrw) * 32 + lane;
+  const bool active = i < S;
+  const int ir = active ? i : S - 1;
+  const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;
+  const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
+  const float scale = rsqrtf((float)HD);
+
+  float s[KPG];
+  float mx = -INFINITY;
+  {
+    float q[HD];
+    row_to_regs<HD>(Qs + ir * HD, q, scale);
+#pragma unroll
+    for (int k = 0; k < KPG; ++k) {
+      const int j = j_beg + k;
+      s[k] = (j < j_end) ? dot_smem<HD>(q, Ks + j * HD) : -INFINITY;
+      mx = fmaxf(mx, s[k]);
+    }
+  }
+  redm[g * S + ir] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(redm[ir], redm[S + ir]), fmaxf(redm[2 * S + ir], redm[3 * S + ir]));
+
+  const bool drop = p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
+  const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
+  const int S4 = (S + 3) & ~3;
+  const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
+  float lsum = 0.f;
+  float acc[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < KPG; k4 += 4) {
+    const int j0 = j_beg + k4;
+    if (j0 < j_end) {
+      float msk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop) dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < j_end) {
+          const float pj = expf(s[k4 + u] - mx);
+          lsum += pj;
+          axpy_row<HD>(pj * msk[u], Vs + (j0 + u) * HD, acc);
+        }
+      }
+    }
+  }
+  reds[g * S + ir] = lsum;
+  if (g > 0) {
+    float* pr = part + ((size_t)(g - 1) * S + ir) * PW;
+#pragma unroll
+    for (int c = 0; c < HD; ++c) pr[c] = acc[c];
+  }
+  __syncthreads();
+  if (g == 0 && active) {
+    lsum = (reds[i] + reds[S + i]) + (reds[2 * S + i] + reds[3 * S + i]);
+#pragma unroll
+    for (int gg = 0; gg < NG - 1; ++gg) {
+      const float* pr = part + ((size_t)gg * S + i) * PW;
+#pragma unroll
+      for (int c = 0; c < HD; ++c) acc[c] += pr[c];
+    }
+    store_row<HD>(o + ((size_t)i * B + b) * d + (size_t)h * HD, acc, 1.f / lsum);
+    lse[(size_t)blockIdx.x * S + i] = mx + logf(lsum);
+  }
+}
+
+//   lane = query i, group = key range:   P_ij, dP_ij, Ps = P m, dSs = P (dP m - D_i) scale   (registers + smem)
+//                                        dQ_i partial = sum_{j in range} dSs_ij k_j            (registers)
+//   lane = key j,   group = query range: dV_j partial = sum_i Ps_ij dO_i,  dK_j partial = sum_i dSs_ij q_i
+template <int HD>
+__global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_bwd_small_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
+    const float* __restrict__ d_o, float* __restrict__ dqkv, int S, int B, int d, int nhead, float p_drop,
+    const Seed seed_ref, uint32_t site) {
+  extern __shared__ __align__(16) float smem[];
+  const int SP = S | 1;
+  constexpr int PW = (2 * HD) | 1;
+  float* Qs = smem;                 // [S][HD]
+  float* Ks = Qs + S * HD;
+  float* Vs = Ks + S * HD;
+  float* dOs = Vs + S * HD;
+  float* Ps = dOs + S * HD;         // [S][SP] dropped, scaled probabilities
+  float* dSs = Ps + S * SP;         // [S][SP]
+  float* part = dSs + S * SP;       // [NG-1][S][PW] partial rows: first dQ (HD wide), later dV | dK (2 HD wide)
+
+  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  const int ld = B * 3 * d;
+  const int ldo = B * d;
+  const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
+  const float* obase = o + (size_t)b * d + (size_t)h * HD;
+  const float* dobase = d_o + (size_t)b * d + (size_t)h * HD;
+  load_tile<HD>(base, ld, Qs, S);
+  load_tile<HD>(base + d, ld, Ks, S);
+  load_tile<HD>(base + 2 * d, ld, Vs, S);
+  load_tile<HD>(dobase, ldo, dOs, S);
+
+  const int nrw = (S + 31) >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = warp / nrw, i = (warp % nrw) * 32 + lane;
+  const bool active = i < S;
+  const int ir = active ? i : S - 1;
+  const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;
+  const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
+  const float scale = rsqrtf((float)HD);
+  const bool drop = p_drop > 0.f;
+  const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
+  const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
+  const int S4 = (S + 3) & ~3;
+  const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
+  const float li = lse[(size_t)blockIdx.x * S + ir];
+  float orow[HD];   // this thread's O row straight from global memory (only D_i needs it)
+  {
+    constexpr int W = Cfg<HD>::W;
+    const float* src = obase + (size_t)ir * ldo;
+#pragma unroll
+    for (int c = 0; c < HD; c += W) {
+      if (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(src + c)); orow[c] = v.x; orow[c + 1] = v.y; orow[c + 2] = v.z; orow[c + 3] = v.w; }
+      else if (W == 2) { const float2 v = __ldg(reinterpret_cast<const float2*>(src + c)); orow[c] = v.x; orow[c + 1] = v.y; }
+      else orow[c] = __ldg(src + c);
+    }
+  }
+  __syncthreads();
+
+  float acc[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) acc[c] = 0.f;
+  {
+    float q[HD], r[HD];
+    row_to_regs<HD>(Qs + ir * HD, q, scale);
+    row_to_regs<HD>(dOs + ir * HD, r, 1.f);
+    float Di = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD; ++c) Di = fmaf(r[c], orow[c], Di);
+#pragma unroll
+    for (int k4 = 0; k4 < KPG; k4 += 4) {
+      const int j0 = j_beg + k4;
+      if (j0 < j_end) {
+        float msk[4] = {1.f, 1.f, 1.f, 1.f};
+        if (drop) dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          if (j < j_end) {
+            const float pj = expf(dot_smem<HD>(q, Ks + j * HD) - li);
+            const float dpd = dot_smem<HD>(r, Vs + j * HD);
+            const float ds = pj * (dpd * msk[u] - Di) * scale;
+            if (active) {
+              Ps[i * SP + j] = pj * msk[u];
+              dSs[i * SP + j] = ds;
+            }
+            axpy_row<HD>(ds, Ks + j * HD, acc);   // dQ_i partial
+          }
+        }
+      }
+    }
+  }
+  if (g > 0) {
+    float* pr = part + ((size_t)(g - 1) * S + ir) * PW;
+#pragma unroll
+    for (int c = 0; c < HD; ++c) pr[c] = acc[c];
+  }
+  __syncthreads();
+  float* out = dqkv + ((size_t)ir * B + b) * 3 * d + (size_t)h * HD;
+  if (g == 0 && active) {
+#pragma unroll
+    for (int gg = 0; gg < NG - 1; ++gg) {
+      const float* pr = part + ((size_t)gg * S + i) * PW;
+#pragma unroll
+      for (int c = 0; c < HD; ++c) acc[c] += pr[c];
+    }
+    store_row<HD>(out, acc, 1.f);
+  }
+  // lane = key j (= ir), group = query range [j_beg, j_end)
+  float accv[HD], acck[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) { accv[c] = 0.f; acck[c] = 0.f; }
+  for (int r = j_beg; r < j_end; ++r) {
+    const float pv = Ps[r * SP + ir], dv = dSs[r * SP + ir];
+    axpy_row<HD>(pv, dOs + r * HD, accv);
+    axpy_row<HD>(dv, Qs + r * HD, acck);
+  }
+  __syncthreads();   // every read of the dQ partials is done: the region is reused for dV | dK
+  if (g > 0) {
+    float* pr = part + ((size_t)(g - 1) * S + ir) * PW;
+#pragma unroll
+    for (int c = 0; c < HD; ++c) { pr[c] = accv[c]; pr[HD + c] = acck[c]; }
+  }
+  __syncthreads();
+  if (g == 0 && active) {
+#pragma unroll
+    for (int gg = 0; gg < NG - 1; ++gg) {
+      const float* pr = part + ((size_t)gg * S + i) * PW;
+#pragma unroll
+      for (int c = 0; c < HD; ++c) { accv[c] += pr[c]; acck[c] += pr[HD + c]; }
+    }
+    store_row<HD>(out + 2 * d, accv, 1.f);
+    store_row<HD>(out + d, acck, 1.f);
+  }
+}
+
 inline int att_threads(int S) { return NG * ((S + 31) / 32) * 32; }
 
 template <int HD>
 int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed, int site,
                cudaStream_t st) {
+  if constexpr (HD <= 16) {
+    auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)2 * NG * s + (size_t)(NG - 1) * s * (HD | 1)) * sizeof(float); };
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(attention_fwd_small_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(GANFFN_MAX_SEQ));
+      attr_done = true;
+    }
+    attention_fwd_small_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
+    GANFFN_LAUNCHED("attention_fwd_small_kernel");
+    return GANFFN_OK;
+  } else {
   auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)s * (s | 1) + (size_t)NG * s) * sizeof(float); };
   static bool attr_done = false;
   if (!attr_done) {
@@ -324,11 +608,24 @@ int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int 
   attention_fwd_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
   GANFFN_LAUNCHED("attention_fwd_kernel");
   return GANFFN_OK;
+  }
 }
 
 template <int HD>
 int launch_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
                int nhead, float p, Seed seed, int site, cudaStream_t st) {
+  if constexpr (HD <= 16) {
+    auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s * (s | 1) + (size_t)(NG - 1) * s * ((2 * HD) | 1)) * sizeof(float); };
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(attention_bwd_small_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(GANFFN_MAX_SEQ));
+      attr_done = true;
+    }
+    attention_bwd_small_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
+                                                                               (uint32_t)site);
+    GANFFN_LAUNCHED("attention_bwd_small_kernel");
+    return GANFFN_OK;
+  } else {
   auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s * (s | 1) + s) * sizeof(float); };
   static bool attr_done = false;
   if (!attr_done) {
@@ -340,6 +637,7 @@ int launch_bwd(const float* qkv, const float* o, const float* lse, const float* 
                                                                        (uint32_t)site);
   GANFFN_LAUNCHED("attention_bwd_kernel");
   return GANFFN_OK;
+  }
 }
 
 }  // namespace

@@ -14,7 +14,7 @@
  *  - `stream` is a cudaStream_t passed as void*.  Nothing here allocates,
  *    synchronises or throws.  Return value: GANFFN_OK or an error code;
  *    ganffn_last_error() gives the text.
- *  - Dropout: counter-based Philox4x32-10 keyed by (seed, site, element).  The same
+ *  - Dropout: counter-based SplitMix64 hash keyed by (seed, site, element group of 4), 16-bit uniforms.  The same
  *    (seed, site) regenerates the same mask in the backward pass; p == 0 is eval mode.
  *    ganffn_dropout_mask() exports the mask a site draws so tests can inject it into
  *    the CPU oracle.
@@ -123,7 +123,7 @@ int ganffn_posenc_fwd(const float* x, const float* pe, float* y, int S, int B, i
                       uint64_t seed, void* stream);
 
 /* Writes out[rows,cols] = the scaled keep mask (0 or 1/(1-p)) that `site` draws; element (r,c)
- * is Philox element r*row_stride + c.  row_stride == cols for every [T,N] site; the attention
+ * is dropout element r*row_stride + c.  row_stride == cols for every [T,N] site; the attention
  * site uses rows = B*nhead*S, cols = S, row_stride = round_up(S,4). */
 int ganffn_dropout_mask(float* out, int64_t rows, int64_t cols, int64_t row_stride, float p_drop,
                         uint64_t seed, int site, void* stream);

@@ -50,11 +50,12 @@ def test_graph_replay_matches_eager_steps():
             H.assert_close(b[k].cpu(), a[k].cpu(), f"step {i} {k}", rtol=1e-4, atol_frac=1e-5)
     # Weights: Adam turns a gradient of magnitude ~0 into a step of +-lr, so the (order-dependent) round-off of the
     # red.global.add accumulation can move individual entries by up to lr per step.  On average the weights must agree
-    # to a small fraction of one step, and no entry may differ by more than the four steps taken.
+    # to a small fraction of one step, and no entry may differ by more than the Adam steps taken: a generator is
+    # stepped three times per call (twice in stage 1, once in stage 2), i.e. twelve times over the four calls.
     wa, wb = results["eager"][1], results["graph"][1]
     diff = (wa - wb).abs()
     lr_max = 1.1e-4
-    assert float(diff.max()) <= 4 * lr_max * 1.01, float(diff.max())
+    assert float(diff.max()) <= 12 * lr_max * 1.01, float(diff.max())
     assert float(diff.mean()) < 0.1 * lr_max, float(diff.mean())
 
 

@@ -1,7 +1,7 @@
 """GPU parity of the whole hot path through the reference-facing module API:
   * every network, GAN_FFN + MaskedNLLLoss, train_disc / train_gen and Adam against the fixtures the
     unmodified reference produced (tests/golden, dropout off);
-  * train mode (dropout on) against the CPU oracle with the kernels' own Philox masks injected;
+  * train mode (dropout on) against the CPU oracle with the kernels' own dropout masks injected;
   * size-independent properties at the full IEMOCAP batch shape (S=94, B=32).
 Tolerance: rtol 1e-4 (north_star), see helpers.RTOL."""
 import numpy as np
@@ -145,7 +145,7 @@ def test_stage1_substeps_and_fused_adam_match_reference_fixture(G, nets, engine)
         disc.zero_grad(set_to_none=True)
 
 
-# ---- train mode: the kernels' Philox masks injected into the oracle -----------------------------------------
+# ---- train mode: the kernels' dropout masks injected into the oracle -----------------------------------------
 def _mask_fn(seed, S, B, nhead, p_head):
     from gan_ffn_b200.functional import dropout_mask
 
