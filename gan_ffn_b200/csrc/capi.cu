@@ -59,7 +59,6 @@ int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_i
     rc = gemm_tc(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
   } else {
     Epilogue e2 = ep;
-    if (e2.atomic_acc) { e2.atomic_acc = 0; e2.beta = 1.0f; }
     e2.rowsum = nullptr;
     rc = gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, e2, scratch, scratch_floats, st);
   }

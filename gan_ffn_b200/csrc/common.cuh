@@ -95,6 +95,22 @@ __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t site, uin
   }
 }
 
+// Loop-hoisted form for 4-aligned element indices: the key and the threshold are computed once per thread.
+struct DropCtx { uint64_t key; uint32_t thr; float scale; };
+__device__ __forceinline__ DropCtx make_drop_ctx(uint64_t seed, uint32_t site, float p) {
+  DropCtx c;
+  c.key = drop_key(seed, site); c.thr = drop_threshold(p); c.scale = 1.0f / (1.0f - p);
+  return c;
+}
+__device__ __forceinline__ void dropout_scale4_aligned(const DropCtx& c, uint64_t e, float out[4]) {
+  const uint64_t w = drop_word(c.key, e >> 2);
+  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  out[0] = (lo & 0xFFFFu) >= c.thr ? c.scale : 0.0f;
+  out[1] = (lo >> 16) >= c.thr ? c.scale : 0.0f;
+  out[2] = (hi & 0xFFFFu) >= c.thr ? c.scale : 0.0f;
+  out[3] = (hi >> 16) >= c.thr ? c.scale : 0.0f;
+}
+
 // ---- activations ---------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
@@ -144,7 +160,8 @@ struct Epilogue {
   float beta = 0.0f;                // C = beta*C + v
   // Gradient accumulation (wgrad): C += v with red.global.add, so split-K slices need no partial buffers and no
   // fold kernel; the tcgen05 engine can also emit rowsum[m] += sum_k A[m,k] (the bias gradient, since A = dY^T)
-  // from the registers of its A producers.  The FFMA engine treats `atomic_acc` as beta = 1 and ignores `rowsum`.
+  // from the registers of its A producers.  The FFMA engine adds with red.global.add too (its split-K fold kernel
+  // or its direct epilogue) and ignores `rowsum`.
   int atomic_acc = 0;
   float* rowsum = nullptr;
 };
@@ -196,6 +213,12 @@ __device__ __forceinline__ void epilogue_store4(const Epilogue& ep, float* C, in
       if (j < nv) v[j] += ep.residual[(size_t)m * ep.ldr + n + j];
   }
   float* c = C + (size_t)m * ldc + n;
+  if (ep.atomic_acc) {   // gradient accumulation: several backward passes may add to C concurrently (network lanes)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) atomicAdd(c + j, v[j]);
+    return;
+  }
   if (ep.beta != 0.0f) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)

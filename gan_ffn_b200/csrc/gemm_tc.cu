@@ -24,6 +24,7 @@
 //               row-contiguous 128-bit global traffic) with a mode-specialised fused epilogue.
 // One full/empty mbarrier pair per stage covers both operand rings (arrivals are per warp, not per
 // thread: 512 arrivals on one mbarrier word serialise for ~1000 cycles per K block).
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace ganffn {
@@ -278,6 +279,77 @@ __device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uin
   }
 }
 
+// ---- lean vector epilogue for the hot flag combinations ------------------------------------------------------------
+// The generic loop in epilogue_subtile() tests its flags at run time and costs ~140 instructions per float4 (SASS,
+// r1); with four warps per scheduler that made the epilogue of a 128 x 128 tile 6 000 of the CTA's 16 000 cycles for
+// the K = 100 products.  Here the flags are template parameters, the dropout counter advances by addition
+// (SplitMix64: state += 4N/4 * gamma per row step) and two row groups are in flight per iteration.
+template <bool BIAS, bool RELU, bool DROP, bool DNZ, bool RES>
+__device__ __forceinline__ void epi_vec(const TcParams& p, uint32_t stage, int m_base, int n, int lane) {
+  const Epilogue& ep = p.ep;
+  const int cq = (lane & 7) * 4, r0 = lane >> 3;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (BIAS) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+  const int m_first = m_base + r0;
+  int rows_left = p.M - m_first;                    // row group i8 is valid iff 4*i8 < rows_left
+  float* cptr = p.C + (size_t)m_first * p.ldc + n;
+  const size_t cstep = (size_t)4 * p.ldc;
+  const float* aux_base = RES ? ep.residual : (DNZ ? ep.dact_src : nullptr);
+  const int aux_ld = RES ? ep.ldr : p.ldc;
+  const float* aptr = (RES || DNZ) ? aux_base + (size_t)m_first * aux_ld + n : nullptr;
+  const size_t astep = (size_t)4 * aux_ld;
+  uint32_t sptr = stage + (uint32_t)(r0 * 36 + cq) * 4;
+  // dropout: word(g) = mix64(key + (g + 1) * gamma), g = (m * N + n) / 4; a row step of 4 adds N to g
+  uint64_t z = 0, zstep = 0;
+  uint32_t thr = 0;
+  float dscale = 1.0f;
+  if (DROP) {
+    const uint64_t key = drop_key(seed_value(ep.seed), ep.site);
+    const uint64_t g = ((uint64_t)m_first * (uint64_t)p.N + (uint64_t)n) >> 2;
+    z = key + (g + 1) * kGamma;
+    zstep = (uint64_t)p.N * kGamma;
+    thr = drop_threshold(ep.p_drop);
+    dscale = 1.0f / (1.0f - ep.p_drop);
+  }
+  const float dact_scale = ep.dact_scale;
+#pragma unroll 2
+  for (int i8 = 0; i8 < 8; ++i8) {
+    if (rows_left > 0) {
+      float4 aux4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (RES || DNZ) aux4 = *reinterpret_cast<const float4*>(aptr);
+      const float4 a4 = lds128(sptr);
+      float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+      if (RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+      if (DROP) {
+        const uint64_t w = mix64(z);
+        const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+        v[0] = (lo & 0xFFFFu) >= thr ? v[0] * dscale : 0.0f;
+        v[1] = (lo >> 16) >= thr ? v[1] * dscale : 0.0f;
+        v[2] = (hi & 0xFFFFu) >= thr ? v[2] * dscale : 0.0f;
+        v[3] = (hi >> 16) >= thr ? v[3] * dscale : 0.0f;
+      }
+      const float ax[4] = {aux4.x, aux4.y, aux4.z, aux4.w};
+      if (DNZ) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ax[j] != 0.0f ? v[j] * dact_scale : 0.0f;
+      }
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += ax[j];
+      }
+      *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    cptr += cstep;
+    if (RES || DNZ) aptr += astep;
+    sptr += 4 * 36 * 4;
+    rows_left -= 4;
+    if (DROP) z += zstep;
+  }
+}
+
 // ---- epilogue of one 32 x 32 sub-tile (already transposed into `stage`, 32 rows x 36 floats) ------------------------
 // Lane -> rows i8*4 + lane/8 (i8 = 0..7), columns (lane%8)*4 .. +3: every global access is a 128-byte row segment.
 template <int EPI>
@@ -341,8 +413,21 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
   const bool relu = EPI == EPI_DROP && ep.act == GANFFN_ACT_RELU;
   const bool drop = EPI == EPI_DROP && ep.p_drop > 0.0f && ep.dact == DACT_NONE;
   const bool dnz = EPI == EPI_DROP && ep.dact == DACT_NONZERO;
-  const float dscale = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
-  const uint64_t seedv = drop ? seed_value(ep.seed) : 0ull;
+  if (!has_beta) {   // hot combinations: compile-time flags (epi_vec); anything else takes the generic loop below
+    const bool hb = ep.bias != nullptr, hr = ep.residual != nullptr;
+    if (EPI == EPI_DROP) {
+      if (hb && relu && drop && !hr) return epi_vec<true, true, true, false, false>(p, stage, m_base, n, lane);
+      if (!hb && !relu && dnz && !hr) return epi_vec<false, false, false, true, false>(p, stage, m_base, n, lane);
+      if (hb && !relu && drop && hr) return epi_vec<true, false, true, false, true>(p, stage, m_base, n, lane);
+    } else {
+      if (hb && !hr) return epi_vec<true, false, false, false, false>(p, stage, m_base, n, lane);
+      if (!hb && hr) return epi_vec<false, false, false, false, true>(p, stage, m_base, n, lane);
+      if (hb && hr) return epi_vec<true, false, false, false, true>(p, stage, m_base, n, lane);
+      if (!hb && !hr) return epi_vec<false, false, false, false, false>(p, stage, m_base, n, lane);
+    }
+  }
+  // N % 4 == 0 on this path, so every element index below is 4-aligned: key / threshold hoisted out of the loop
+  const DropCtx dctx = drop ? make_drop_ctx(seed_value(ep.seed), ep.site, ep.p_drop) : DropCtx{0ull, 0u, 1.0f};
   // Software pipeline (the residual / dact source / old C of row group i8+1 is in flight while i8 is computed) with
   // strength-reduced pointers: the loop is issue-bound, 16 warps run it at once.
   const int m_first = m_base + r0;
@@ -374,7 +459,7 @@ __device__ __forceinline__ void epilogue_subtile(const TcParams& p, uint32_t sta
     }
     if (drop) {
       float msk[4];
-      dropout_scale4(seedv, ep.site, eidx, ep.p_drop, dscale, msk);
+      dropout_scale4_aligned(dctx, eidx, msk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] *= msk[j];
     }
@@ -600,6 +685,241 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
   }
 }
 
+// ---- A-stationary variant: K <= 128, wide N ---------------------------------------------------------------------
+// The d=100 networks' two widest products -- linear1 forward ([T,100] x [100,2048]) and its mirror in the backward
+// pass (dH = dZ W2, same shape) -- have four K blocks per 128 x 128 tile: the generic kernel above spends its life in
+// prologue, first-load latency and epilogue (ncu r1: 36-41 us for 1.2 GFLOP, 384 CTAs in 2.6 waves, nothing
+// overlapped across CTAs because each owns the SM's whole TMEM and 197 KB of smem).  Here one CTA owns a 128-row
+// block of A for its whole life: A (hi | lo, all of K) is written to TMEM once, then the CTA walks over 64-wide N
+// tiles with B tiles double-buffered in shared memory and the accumulators double-buffered in TMEM, so the MMAs of
+// tile i+1 run under the epilogue of tile i:
+//   warps 0-7   load A once (same tcgen05.st path as above), then are the epilogue warps (TMEM -> registers ->
+//               smem transpose -> fused epilogue -> row-contiguous global stores)
+//   warps 8-15  B producers: all K blocks of one 64-wide tile per stage (64 KB), two stages
+//   warp 16     MMA issuer: 3 x ceil(K/8) MMAs per tile into accumulator buffer (tile & 1)
+// TMEM: [0,128) accumulators of buffer 0 (main | corr), [128,256) buffer 1, [256,512) A (4 K blocks x (32 hi | 32 lo)).
+constexpr int ABN = 64;
+constexpr int AKB = 4;
+constexpr int AB_TILE = ABN * BK * 4;          // one hi (or lo) tile of one K block: 8 KB
+constexpr int AB_KB = 2 * AB_TILE;
+constexpr int AB_STAGE = AKB * AB_KB;          // 64 KB
+constexpr int ASTAGES = 2;
+constexpr int A_EPI = NAW * 32 * 36 * 4;
+constexpr int ASMEM = ASTAGES * AB_STAGE + A_EPI + 1024 + 256;
+constexpr int ATM_A = 256;
+constexpr int ANBW = 4;                        // B producer warps (13 warps per CTA: up to 152 registers per thread)
+constexpr int ANPW = NAW + ANBW;
+constexpr int A_NTHREADS = (ANPW + 1) * 32;
+static_assert(ASMEM <= 227 * 1024, "smem budget");
+
+template <bool TB, int EPI>
+__global__ void __launch_bounds__(A_NTHREADS, 1) gemm_tc_astat_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* epi_smem = smem + ASTAGES * AB_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + A_EPI);
+  uint64_t* a_full = bars;                    // A producers -> MMA (once)
+  uint64_t* b_full = bars + 1;                // [2] B producers -> MMA
+  uint64_t* b_empty = bars + 3;               // [2] MMA -> B producers
+  uint64_t* acc_full = bars + 5;              // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 7;             // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  if (t == 0) TR(0);
+  const int m0 = blockIdx.y * BM;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int ntiles = (p.N + ABN - 1) / ABN;
+
+  if (t == 0) {
+    mbar_init(smem_u32(a_full), NAW);
+    for (int s = 0; s < ASTAGES; ++s) {
+      mbar_init(smem_u32(b_full + s), ANBW);
+      mbar_init(smem_u32(b_empty + s), 1);
+      mbar_init(smem_u32(acc_full + s), 1);
+      mbar_init(smem_u32(acc_empty + s), NAW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == ANPW) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (t == 0) TR(1);
+
+  if (warp < NAW) {
+    const int quad = warp & 3, half = warp >> 2;
+    const int row_base = m0 + quad * 32;
+    {
+      // ================= A: global -> registers -> TMEM, all K blocks, once =================
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ATM_A + half * 16);
+      const float* ap = p.A + (size_t)(row_base + (lane >> 2)) * p.lda + half * 16 + 2 * (lane & 3);
+      const int a_rows_left = p.M - (row_base + (lane >> 2));
+      const int a_k0 = half * 16 + 2 * (lane & 3);
+      float buf[AKB][16];
+#pragma unroll
+      for (int kb = 0; kb < AKB; ++kb)
+        if (kb < nkb) load_a<true>(buf[kb], ap + kb * BK, p.lda, a_rows_left, p.K - (a_k0 + kb * BK));
+#pragma unroll
+      for (int kb = 0; kb < AKB; ++kb)
+        if (kb < nkb) store_a<true>(buf[kb], trow + (uint32_t)(kb * 64));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(a_full));
+      if (t == 0) TR(2);
+    }
+    // ================= epilogue: warp -> lane quadrant warp%4, columns 32*(warp/4) .. +31 of the 64-wide tile ==========
+    const int col0 = half * 32;
+    const uint32_t stage = smem_u32(epi_smem) + (uint32_t)(warp * (32 * 36) * 4);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      const int n0 = tile * ABN;
+      mbar_wait(smem_u32(acc_full + s), ph);
+      tc_fence_after();
+      if (t == 0 && it < 8) TR(8 + it);
+      const bool live = n0 + col0 < p.N;
+      uint32_t r[32], rl[32];
+      if (live) {
+        const uint32_t tr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 2 * ABN + col0);
+        tmem_ld32(tr, r);
+        tmem_ld32(tr + ABN, rl);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(acc_empty + s));   // the accumulator buffer is free again
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float ox = __uint_as_float(r[4 * q]) + __uint_as_float(rl[4 * q]);
+          const float oy = __uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]);
+          const float oz = __uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]);
+          const float ow = __uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]);
+          sts128(stage + (uint32_t)(lane * 36 + q * 4) * 4, __float_as_uint(ox), __float_as_uint(oy), __float_as_uint(oz),
+                 __float_as_uint(ow));
+        }
+        __syncwarp();
+        epilogue_subtile<EPI>(p, stage, row_base, n0 + col0, lane, 0);
+        __syncwarp();   // the transpose buffer is rewritten by the next tile
+      }
+      if (t == 0 && it < 8) TR(80 + it);
+    }
+    tc_fence_before();
+  } else if (warp < ANPW) {
+    // ================= B producers: one 64-wide tile (all K blocks) per stage =================
+    const int tb = t - NAW * 32;
+    int64_t g_off, g_istride, g_kstep, g_nstep;
+    int rows_off, k_off, i_rows, i_k;   // validity: row/k offsets of chunk 0 and their step per chunk index
+    uint32_t b_off;
+    if (TB) {   // K-major: element (n, k) at B[n * ldb + k]
+      const int r = tb >> 3, c = tb & 7;   // rows r + 16 i
+      g_off = (int64_t)r * p.ldb + 4 * c; g_istride = (int64_t)16 * p.ldb; g_kstep = BK; g_nstep = (int64_t)ABN * p.ldb;
+      rows_off = r; k_off = 4 * c; i_rows = 16; i_k = 0;
+      b_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    } else {    // MN-major: element (n, k) at B[k * ldb + n]
+      const int k = tb >> 4, mq = tb & 15;   // k + 8 i
+      g_off = (int64_t)k * p.ldb + 4 * mq; g_istride = (int64_t)8 * p.ldb; g_kstep = (int64_t)BK * p.ldb; g_nstep = ABN;
+      rows_off = 4 * mq; k_off = k; i_rows = 0; i_k = 8;
+      b_off = (uint32_t)(((k >> 2) * (ABN / 32) + (mq >> 3)) * 512 + (k & 3) * 128 + ((((mq & 7) >> 1) ^ (k & 3)) << 5) +
+                         ((mq & 1) << 4));
+    }
+    const uint32_t b_smem = smem_u32(smem) + b_off;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      const int n0 = tile * ABN;
+      const float* bp = p.B + g_off + (int64_t)tile * g_nstep;
+      float4 v[AKB][4];
+#pragma unroll
+      for (int kb = 0; kb < AKB; ++kb)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[kb][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool ok = kb < nkb && (n0 + rows_off + i * i_rows < p.N) && (kb * BK + k_off + i * i_k < p.K);
+          if (ok) v[kb][i] = __ldg(reinterpret_cast<const float4*>(bp + kb * g_kstep + i * g_istride));
+        }
+      mbar_wait(smem_u32(b_empty + s), ph ^ 1u);
+#pragma unroll
+      for (int kb = 0; kb < AKB; ++kb) {
+        if (kb < nkb) {
+          const uint32_t hi = b_smem + (uint32_t)(s * AB_STAGE + kb * AB_KB);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x[4] = {v[kb][i].x, v[kb][i].y, v[kb][i].z, v[kb][i].w};
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              h[j] = tf32_rna(x[j]);
+              l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));
+            }
+            sts128(hi + i * 2048, h[0], h[1], h[2], h[3]);
+            sts128(hi + AB_TILE + i * 2048, l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(b_full + s));
+      if (tb == 0 && it < 8) TR(24 + it);
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t b_lbo = TB ? 16 : 512, b_sbo = TB ? 1024 : (ABN / 32) * 512, b_lt = TB ? 2u : 1u;
+      const uint64_t bdesc0 = make_desc(smem_u32(smem), b_lbo, b_sbo, b_lt);
+      const uint32_t bdesc_hi32 = (uint32_t)(bdesc0 >> 32), bdesc_lo32 = (uint32_t)bdesc0;
+      constexpr uint32_t B_JSTEP = (TB ? 32u : 2u * (ABN / 32) * 512u) >> 4;
+      mbar_wait(smem_u32(a_full), 0);
+      tc_fence_after();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        const int n0 = tile * ABN;
+        const int n_mma = min(ABN, (int)((p.N - n0 + 15) & ~15));
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TB ? 0u : 1u) << 16) | ((uint32_t)(n_mma >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+        mbar_wait(smem_u32(acc_empty + s), ph ^ 1u);
+        mbar_wait(smem_u32(b_full + s), ph);
+        tc_fence_after();
+        if (it < 8) TR(48 + 2 * it);
+        const uint32_t d_main = tmem_base + (uint32_t)(s * 2 * ABN), d_corr = d_main + ABN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t b_lo32 = bdesc_lo32 + (uint32_t)((s * AB_STAGE + kb * AB_KB) >> 4);
+          const uint32_t a_hi = tmem_base + (uint32_t)(ATM_A + kb * 64);
+          const int ksteps = min(BK / 8, (p.K - kb * BK + 7) >> 3);
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            if (j < ksteps) {
+              const uint64_t dbh = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP);
+              const uint64_t dbl = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP + (AB_TILE >> 4));
+              const uint32_t acc = (j > 0 || kb > 0) ? 1u : 0u;
+              umma_tf32_ts(d_corr, a_hi + 32 + 8 * j, dbh, idesc, acc);
+              umma_tf32_ts(d_corr, a_hi + 8 * j, dbl, idesc, 1u);
+              umma_tf32_ts(d_main, a_hi + 8 * j, dbh, idesc, acc);
+            }
+          }
+        }
+        umma_commit(smem_u32(b_empty + s));
+        umma_commit(smem_u32(acc_full + s));
+        if (it < 8) TR(49 + 2 * it);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (t == 0) TR(6);
+  if (warp == ANPW) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
 __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* C,
                                                                int ldc, int M, int N, int Np, const Epilogue ep) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -679,6 +999,29 @@ int launch_tc(const TcParams& p, bool TA, bool TB, int epi, dim3 grid, cudaStrea
   return launch_tc2<true, true>(p, epi, grid, st);
 }
 
+template <bool TB>
+int launch_astat2(const TcParams& p, int epi, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_astat_kernel<TB, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMEM);
+    cudaFuncSetAttribute(gemm_tc_astat_kernel<TB, EPI_DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMEM);
+    cudaFuncSetAttribute(gemm_tc_astat_kernel<TB, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMEM);
+    attr_done = true;
+  }
+  if (epi == EPI_PLAIN) gemm_tc_astat_kernel<TB, EPI_PLAIN><<<grid, A_NTHREADS, ASMEM, st>>>(p);
+  else if (epi == EPI_DROP) gemm_tc_astat_kernel<TB, EPI_DROP><<<grid, A_NTHREADS, ASMEM, st>>>(p);
+  else gemm_tc_astat_kernel<TB, EPI_FULL><<<grid, A_NTHREADS, ASMEM, st>>>(p);
+  GANFFN_LAUNCHED("gemm_tc_astat_kernel");
+  return GANFFN_OK;
+}
+
+// K <= 128 and at least four 64-wide N tiles: one pass over A per CTA pays.
+inline bool astat_applies(bool transA, int M, int N, int K, const Epilogue& ep) {
+  static const bool off = getenv("GANFFN_NO_ASTAT") != nullptr;   // A/B switch for profiling
+  if (off) return false;
+  return !transA && K <= AKB * BK && N >= 4 * ABN && M >= 96 && !ep.atomic_acc && ep.rowsum == nullptr;
+}
+
 inline bool al16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
 
 // Which epilogue specialisation can serve this call.
@@ -722,6 +1065,17 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     p.M = M; p.N = N; p.K = K; p.k_per_split = pa.kps; p.partial = nullptr; p.Np = Np; p.ep = ep;
     p.out_mode = ((N & 3) == 0 && (ldc & 3) == 0 && al16(C)) ? 2 : 3;
     return launch_tc(p, transA, b_is_nk, EPI_PLAIN, dim3(cdiv(N, BN), cdiv(M, BM), pa.splits), st);
+  }
+  if (astat_applies(transA, M, N, K, ep)) {
+    TcParams p;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.k_per_split = (int)round_up(K, BK); p.partial = nullptr; p.Np = Np; p.ep = ep;
+    p.out_mode = 0;
+    const int mtiles = cdiv(M, BM), ntiles = cdiv(N, ABN);
+    const int groups = std::max(1, std::min(ntiles, 148 / std::max(1, mtiles)));
+    const int epi = pick_epilogue(ep, C, ldc, N);
+    return b_is_nk ? launch_astat2<true>(p, epi, dim3(groups, mtiles, 1), st)
+                   : launch_astat2<false>(p, epi, dim3(groups, mtiles, 1), st);
   }
   TcPlan pl = tc_plan(M, N, K);
   if (pl.splits > 1 && (scratch == nullptr || scratch_floats < (int64_t)pl.splits * M * Np)) {

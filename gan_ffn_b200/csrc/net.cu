@@ -4,6 +4,10 @@
 //
 // Reference: generators model.py:1221-1231, 1255-1263, 1286-1294; discriminators model.py:1320-1327,
 // 1354-1364, 1390-1397; encoder layer torch/nn/modules/transformer.py:944-982 (post-norm, ReLU).
+#include <map>
+#include <mutex>
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace ganffn {
@@ -51,7 +55,7 @@ Stash stash_layout(const NetDims& nd) {
 }
 
 struct Scratch {
-  int64_t da, db, dz, dzd, d_o, dqkv, dh, hb1, hb2, hb3, gemm, gemm_floats, red, total;
+  int64_t da, db, dz, dzd, dz1, dzd1, d_o, dqkv, dh, hb1, hb2, hb3, gemm, gemm_floats, gemm2, red, total;
 };
 
 Scratch scratch_layout(const NetDims& nd) {
@@ -62,6 +66,8 @@ Scratch scratch_layout(const NetDims& nd) {
   s.db = p; p += al(T * d);
   s.dz = p; p += al(T * d);
   s.dzd = p; p += al(T * d);
+  s.dz1 = p; p += al(T * d);     // LayerNorm-1 backward writes its own pair, so the weight-gradient stream can still
+  s.dzd1 = p; p += al(T * d);    // be reading the LayerNorm-2 pair (and vice versa)
   s.d_o = p; p += al(T * d);
   s.dqkv = p; p += al(T * 3 * d);
   s.dh = p; p += al(T * nd.dff);
@@ -81,6 +87,7 @@ Scratch scratch_layout(const NetDims& nd) {
   mx(3 * nd.d, nd.d, Ti); mx(nd.d, nd.d, Ti); mx(nd.dff, nd.d, Ti); mx(nd.d, nd.dff, Ti);
   mx(nd.h1, nd.d, Ti); mx(nd.h2, nd.h1, Ti); mx(1, nd.h2, Ti);
   s.gemm = p; s.gemm_floats = al(g); p += s.gemm_floats;
+  s.gemm2 = p; p += s.gemm_floats;   // workspace of the weight-gradient stream
   s.red = p; p += al(32);
   s.total = p;
   return s;
@@ -105,6 +112,41 @@ struct Ctx {
     return linear_wgrad(dy, x, dw, dbias, M, N, K, 1, gemm_scratch, gemm_floats, st);
   }
 };
+
+// ---- weight-gradient side stream -----------------------------------------------------------------------------------
+// In the backward pass only the data gradients are on the critical path (LN -> dgrad -> dgrad -> LN -> dgrad ->
+// attention -> dgrad per layer); the four weight-gradient products of a layer just have to be finished before the
+// optimizer runs.  They are issued on a second stream that forks from / joins the caller's stream with events (legal
+// inside CUDA-graph capture), so they fill SMs the 24..144-CTA data-gradient kernels leave idle.  One side stream
+// per caller stream (networks on different lanes each get their own); created on first use, never destroyed.
+struct SideCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ready[4], done[4], join;   // slots: L2, L1, OUT, IN
+  bool pending[4] = {false, false, false, false};
+};
+enum { W_L2 = 0, W_L1 = 1, W_OUT = 2, W_IN = 3 };
+
+SideCtx* side_ctx(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<cudaStream_t, SideCtx*> table;
+  static const bool off = getenv("GANFFN_NO_WGRAD_STREAM") != nullptr;
+  if (off) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = table.find(st);
+  if (it != table.end()) return it->second;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return nullptr;   // never create streams/events while capturing
+  SideCtx* c = new SideCtx();
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  for (int i = 0; i < 4; ++i) {
+    cudaEventCreateWithFlags(&c->ready[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming);
+  table[st] = c;
+  return c;
+}
 
 }  // namespace
 
@@ -259,37 +301,69 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
   }
 
   // ---- encoder layers, last to first ----
+  // Data gradients on the caller's stream, weight gradients on the side stream (see SideCtx).  wait_slot(k) orders a
+  // kernel that overwrites the input of a still-pending weight-gradient product of slot k behind that product.
+  SideCtx* sx = side_ctx(st);
+  float* gemm2 = scratch + sc.gemm2;
+  float* dz1 = scratch + sc.dz1;
+  float* dzd1_buf = scratch + sc.dzd1;
+  if (sx) for (int i = 0; i < 4; ++i) sx->pending[i] = false;
+  auto wgrad_side = [&](int slot, const float* dy, const float* xa, float* dw, float* dbias, int M, int N, int K) -> int {
+    if (!sx) return cx.wgrad(dy, xa, dw, dbias, M, N, K, accumulate);
+    cudaEventRecord(sx->ready[slot], st);
+    cudaStreamWaitEvent(sx->side, sx->ready[slot], 0);
+    const int rc = linear_wgrad(dy, xa, dw, dbias, M, N, K, 1, gemm2, sc.gemm_floats, sx->side);
+    cudaEventRecord(sx->done[slot], sx->side);
+    sx->pending[slot] = true;
+    return rc;
+  };
+  auto wait_slot = [&](int slot) {
+    if (sx && sx->pending[slot]) {
+      cudaStreamWaitEvent(st, sx->done[slot], 0);
+      sx->pending[slot] = false;
+    }
+  };
   for (int l = nd.L - 1; l >= 0; --l) {
     const float* base = stash + sl.layer0 + (int64_t)l * sl.per_layer;
     const int64_t* lo = off + (int64_t)l * PER_LAYER;
     const float* xin = l == 0 ? stash + sl.x0 : stash + sl.layer0 + (int64_t)(l - 1) * sl.per_layer + sl.x2;
     float* dzd = p_enc > 0.f ? dzd_buf : dz;
+    float* dzd1 = p_enc > 0.f ? dzd1_buf : dz1;
 
     // x2 = LN2(z2), z2 = x1 + drop(linear2(h))
+    wait_slot(W_L2);
     GANFFN_TRY(layernorm_bwd(da, base + sl.z2, P(lo[N2_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N2_W]), G(lo[N2_B]),
                              G(lo[L2_B]), T, d, 1, p_enc, seed, GANFFN_SITE_LAYER(l, 3), st));
-    GANFFN_TRY(cx.wgrad(dzd, base + sl.h, G(lo[L2_W]), nullptr, T, d, nd.dff, accumulate));
+    GANFFN_TRY(wgrad_side(W_L2, dzd, base + sl.h, G(lo[L2_W]), nullptr, T, d, nd.dff));
+    wait_slot(W_L1);
     {
       Epilogue ep; ep.dact = DACT_NONZERO; ep.dact_src = base + sl.h; ep.dact_scale = p_enc > 0.f ? 1.f / (1.f - p_enc) : 1.f;
       GANFFN_TRY(cx.dgrad(dzd, P(lo[L2_W]), scratch + sc.dh, T, d, nd.dff, ep));
     }
-    GANFFN_TRY(cx.wgrad(scratch + sc.dh, base + sl.x1, G(lo[L1_W]), G(lo[L1_B]), T, nd.dff, d, accumulate));
+    GANFFN_TRY(wgrad_side(W_L1, scratch + sc.dh, base + sl.x1, G(lo[L1_W]), G(lo[L1_B]), T, nd.dff, d));
     {
       Epilogue ep; ep.residual = dz; ep.ldr = d;
       GANFFN_TRY(cx.dgrad(scratch + sc.dh, P(lo[L1_W]), db, T, nd.dff, d, ep));
     }
     // x1 = LN1(z1), z1 = xin + drop(out_proj(o))
-    GANFFN_TRY(layernorm_bwd(db, base + sl.z1, P(lo[N1_W]), dz, p_enc > 0.f ? dzd_buf : nullptr, G(lo[N1_W]), G(lo[N1_B]),
+    wait_slot(W_OUT);
+    GANFFN_TRY(layernorm_bwd(db, base + sl.z1, P(lo[N1_W]), dz1, p_enc > 0.f ? dzd1_buf : nullptr, G(lo[N1_W]), G(lo[N1_B]),
                              G(lo[OUT_B]), T, d, 1, p_enc, seed, GANFFN_SITE_LAYER(l, 1), st));
-    GANFFN_TRY(cx.wgrad(dzd, base + sl.o, G(lo[OUT_W]), nullptr, T, d, d, accumulate));
-    GANFFN_TRY(cx.dgrad(dzd, P(lo[OUT_W]), scratch + sc.d_o, T, d, d, Epilogue{}));
+    GANFFN_TRY(wgrad_side(W_OUT, dzd1, base + sl.o, G(lo[OUT_W]), nullptr, T, d, d));
+    GANFFN_TRY(cx.dgrad(dzd1, P(lo[OUT_W]), scratch + sc.d_o, T, d, d, Epilogue{}));
+    wait_slot(W_IN);
     GANFFN_TRY(attention_bwd(base + sl.qkv, base + sl.o, base + sl.lse, scratch + sc.d_o, scratch + sc.dqkv, nd.S, nd.B,
                              d, nd.nhead, p_enc, seed, GANFFN_SITE_LAYER(l, 0), st));
-    GANFFN_TRY(cx.wgrad(scratch + sc.dqkv, xin, G(lo[IN_W]), G(lo[IN_B]), T, 3 * d, d, accumulate));
+    GANFFN_TRY(wgrad_side(W_IN, scratch + sc.dqkv, xin, G(lo[IN_W]), G(lo[IN_B]), T, 3 * d, d));
     {
-      Epilogue ep; ep.residual = dz; ep.ldr = d;
+      Epilogue ep; ep.residual = dz1; ep.ldr = d;
       GANFFN_TRY(cx.dgrad(scratch + sc.dqkv, P(lo[IN_W]), da, T, 3 * d, d, ep));
     }
+  }
+  if (sx) {   // join: every weight gradient has landed before the caller's stream continues
+    cudaEventRecord(sx->join, sx->side);
+    cudaStreamWaitEvent(st, sx->join, 0);
+    for (int i = 0; i < 4; ++i) sx->pending[i] = false;
   }
 
   // ---- positional encoding (dropout only) and the optional `object` projection ----

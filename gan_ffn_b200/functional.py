@@ -112,6 +112,11 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 _scratch: Dict[Tuple[str, int], torch.Tensor] = {}
 
 
+def _scratch_tag(device: torch.device) -> str:
+    """One workspace per stream: networks on different lanes run concurrently."""
+    return "main" if not _lanes.active else f"s{torch.cuda.current_stream(device).cuda_stream}"
+
+
 def scratch(device: torch.device, floats: int, tag: str = "main") -> torch.Tensor:
     """A grow-only workspace per (device, tag).  All kernels of this package are issued on
     the current stream, so one workspace per device is safe to share between calls."""
@@ -121,6 +126,86 @@ def scratch(device: torch.device, floats: int, tag: str = "main") -> torch.Tenso
         buf = torch.empty(max(int(floats), 1), dtype=torch.float32, device=device)
         _scratch[key] = buf
     return buf
+
+
+# --------------------------------------------------------------------------------------
+# network lanes: independent networks of one loop body on concurrent streams
+# --------------------------------------------------------------------------------------
+class _Lanes:
+    """Inside ``overlap_networks()`` every whole-network call (``net_forward``) is issued on one of ``n`` side
+    streams ("lanes", round-robin) instead of the caller's stream, so that networks that do not depend on each
+    other overlap on the device: ``disc(real)`` with ``gen(real_gen)`` and the two discriminator backward passes
+    of ``train_disc`` (train_IEMOCAP.py:217-225), the three generators of ``GAN_FFN.forward`` (model.py:1440-1442)
+    and their backward passes.  At S*B = 3008 slots most kernels of the d=100 networks are 24..144-CTA grids on a
+    148-SM device, so two or three of them fit side by side.
+
+    Ordering rules (all device-side, capturable into a CUDA graph):
+      * fork: a lane waits for everything already enqueued on the caller's stream, and for the producing lane of
+        its input when that was another network of the same context;
+      * join: every other entry point of this package (losses, fuse_classify, optimizer step, context exit) first
+        makes the caller's stream wait for all lanes that carry un-joined work;
+      * backward: autograd runs each network's backward on the lane its forward ran on and orders gradient
+        hand-overs between streams itself.
+    Only code that consumes network outputs through this package's own entry points may run inside the context
+    (the two loop bodies of train.py do); a plain torch op on a network output would not wait for its lane."""
+
+    def __init__(self):
+        self.active = False
+        self.n = 3
+        self.streams: Dict[int, List[torch.cuda.Stream]] = {}
+        self.busy: Dict[int, torch.cuda.Stream] = {}
+        self.producers: Dict[int, Tuple[torch.cuda.Event, torch.cuda.Stream]] = {}
+        self.counter = 0
+
+    def lane(self, device: torch.device) -> Tuple[int, torch.cuda.Stream]:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        pool = self.streams.get(idx)
+        if pool is None:
+            pool = [torch.cuda.Stream(device=device) for _ in range(self.n)]
+            self.streams[idx] = pool
+        k = self.counter % self.n
+        self.counter += 1
+        return k, pool[k]
+
+    def touch(self, stream: torch.cuda.Stream) -> None:
+        self.busy[stream.cuda_stream] = stream
+
+    def join(self) -> None:
+        """The caller's current stream waits for all lanes with un-joined work."""
+        if not self.busy:
+            return
+        main = torch.cuda.current_stream()
+        for st in self.busy.values():
+            if st.cuda_stream != main.cuda_stream:
+                main.wait_stream(st)
+        self.busy.clear()
+        self.producers.clear()
+
+
+_lanes = _Lanes()
+
+
+class overlap_networks:
+    """Context manager: run the networks called inside on concurrent lanes (see ``_Lanes``)."""
+
+    def __init__(self, enabled: bool = True, lanes: int = 3):
+        self.enabled, self.lanes = enabled, lanes
+
+    def __enter__(self):
+        self.prev = _lanes.active
+        if self.enabled:
+            _lanes.n = self.lanes
+            _lanes.active = True
+        return self
+
+    def __exit__(self, *exc):
+        _lanes.join()
+        _lanes.active = self.prev
+        return False
+
+
+def join_lanes() -> None:
+    _lanes.join()
 
 
 def _al(n: int, a: int = 32) -> int:
@@ -158,6 +243,15 @@ class ParamArena:
         self.numel = total
         self.sentinel = params[0]
         self.requires_grad = any(p.requires_grad for p in params)
+        self.prezeroed = False      # FusedAdam.zero_grad() already cleared ``grad`` on the caller's stream
+        self.zero_event, self.zero_stream = None, None
+
+    def prezero(self) -> None:
+        """zero_grad(set_to_none=True) for an arena: the ``.grad`` views are dropped by the caller; the buffer is
+        cleared now, on the caller's stream, so that backward passes on several lanes can accumulate into it."""
+        self.grad.zero_()
+        self.prezeroed = True
+        self.zero_event, self.zero_stream = None, None
 
     def valid_for(self, dev: torch.device) -> bool:
         o = 0
@@ -200,7 +294,7 @@ class _NetFunction(torch.autograd.Function):
         stash_n = L.query("ganffn_net_stash_floats", *dims)
         scratch_n = L.query("ganffn_net_scratch_floats", *dims)
         stash = torch.empty(stash_n, dtype=torch.float32, device=x.device)
-        ws = scratch(x.device, scratch_n)
+        ws = scratch(x.device, scratch_n, _scratch_tag(x.device))
         out = torch.empty((S, B, spec.h2 if spec.kind == 0 else 1), dtype=torch.float32, device=x.device)
         L.call("ganffn_net_fwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(pe), ptr(x), ptr(out),
                ptr(stash), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff, spec.nlayers, spec.h1, spec.h2,
@@ -217,13 +311,24 @@ class _NetFunction(torch.autograd.Function):
         S, B, d_in = x.shape
         dims = spec.dims(S, B, d_in)
         d_out = d_out.contiguous()
-        ws = scratch(x.device, L.query("ganffn_net_scratch_floats", *dims))
+        ws = scratch(x.device, L.query("ganffn_net_scratch_floats", *dims), _scratch_tag(x.device))
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        cur = torch.cuda.current_stream(x.device)
+        if _lanes.active:
+            _lanes.touch(cur)
         if not arena.grads_live():
             # Parameter gradients are accumulated by the kernels (red.global.add from the wgrad GEMMs and the
-            # LayerNorm backward), torch-style: a fresh backward starts from a zeroed arena (one memset).
-            arena.grad.zero_()
+            # LayerNorm backward), torch-style: a fresh backward starts from a zeroed arena (one memset) -- done
+            # by FusedAdam.zero_grad() on the caller's stream (``prezeroed``), else here.
+            if not arena.prezeroed:
+                arena.grad.zero_()
+                arena.zero_event = torch.cuda.Event()
+                arena.zero_event.record(cur)
+                arena.zero_stream = cur.cuda_stream
+            arena.prezeroed = False
             arena.install_grads()
+        elif arena.zero_event is not None and arena.zero_stream != cur.cuda_stream:
+            cur.wait_event(arena.zero_event)   # another lane zeroed the arena for this backward pass
         L.call("ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
                ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
                spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, ctx.seed_ptr, 1, _stream(x))
@@ -245,7 +350,23 @@ def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Ten
     anchor = arena.flat
     if arena.requires_grad and torch.is_grad_enabled():
         anchor = arena.flat.detach().requires_grad_(True)  # makes autograd call backward even for data inputs
-    return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr)
+    if not _lanes.active:
+        return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr)
+    main = torch.cuda.current_stream(x.device)
+    k, lane = _lanes.lane(x.device)
+    lane.wait_stream(main)                                   # fork
+    src = _lanes.producers.get(x.untyped_storage().data_ptr())
+    if src is not None and src[1].cuda_stream != lane.cuda_stream:
+        lane.wait_event(src[0])                              # input made by another network still on its lane
+    x.record_stream(lane)
+    with torch.cuda.stream(lane):
+        out = _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr)
+        ev = torch.cuda.Event()
+        ev.record(lane)
+    out.record_stream(main)
+    _lanes.producers[out.untyped_storage().data_ptr()] = (ev, lane)
+    _lanes.touch(lane)
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -286,6 +407,7 @@ class _FuseClsFunction(torch.autograd.Function):
 def fuse_classify(a, v, t, w, b):
     for z in (a, v, t, w, b):
         _require_cuda(z, "fuse_classify")
+    _lanes.join()
     return _FuseClsFunction.apply(a, v, t, w, b)
 
 
@@ -320,6 +442,7 @@ class _MaskedNLLFunction(torch.autograd.Function):
 
 def masked_nll(pred, target, mask, weight=None, den_override: float = 0.0):
     _require_cuda(pred, "MaskedNLLLoss pred")
+    _lanes.join()
     if pred.dim() != 2:
         raise ValueError(f"MaskedNLLLoss: pred must be (batch*seq_len, n_classes), got {tuple(pred.shape)}")
     target = target.reshape(-1).to(torch.int64).contiguous()
@@ -355,6 +478,7 @@ class _BCEFunction(torch.autograd.Function):
 
 def bce(prob, target, scale: float = 1.0):
     _require_cuda(prob, "BCELoss input")
+    _lanes.join()
     if prob.shape != target.shape:
         raise ValueError(f"BCELoss: input {tuple(prob.shape)} and target {tuple(target.shape)} differ")
     target = target.to(device=prob.device, dtype=torch.float32)

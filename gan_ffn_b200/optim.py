@@ -61,12 +61,16 @@ class FusedAdam:
 
     # -- torch.optim API surface the reference loop uses ------------------------------------
     def zero_grad(self, set_to_none: bool = True):
+        GF.join_lanes()
         for mod in self.modules:
             for p in mod.parameters():
                 if set_to_none:
                     p.grad = None
                 elif p.grad is not None:
                     p.grad.zero_()
+        if set_to_none:
+            for ar in self._arenas():
+                ar.prezero()   # one memset now, on the caller's stream, instead of one inside the first backward
 
     def _state_for(self, key, like: torch.Tensor):
         """Adam state of an arena / loose parameter.  The step count lives on the device (``step_t``) and is bumped by
@@ -84,6 +88,7 @@ class FusedAdam:
     @torch.no_grad()
     def step(self):
         L = lib()
+        GF.join_lanes()   # backward passes issued on network lanes must have landed in the gradient arenas
         lr = self.param_groups[0]["lr"]
         b1, b2 = self.betas
         arenas = self._arenas()

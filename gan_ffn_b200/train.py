@@ -16,6 +16,7 @@ from typing import Dict
 
 import torch
 
+from . import functional as GF
 from . import model as M
 from .optim import FusedAdam
 from .synthetic import Batch
@@ -60,7 +61,7 @@ class GANTrainer:
     optimizers (generators lr, discriminators lr/2, text generator lr*1.1), BCE adversarial loss."""
 
     def __init__(self, acoustic_gen, visual_gen, text_gen, acoustic_disc, visual_disc, text_disc, lr=GAN_LR, b1=GAN_B1,
-                 b2=GAN_B2, grad_reducer=None, world_size: int = 1):
+                 b2=GAN_B2, grad_reducer=None, world_size: int = 1, overlap: bool = True):
         self.nets = dict(acoustic_gen=acoustic_gen, visual_gen=visual_gen, text_gen=text_gen, acoustic_disc=acoustic_disc,
                          visual_disc=visual_disc, text_disc=text_disc)
         mk = lambda net, rate: FusedAdam(net, lr=rate, betas=(b1, b2), grad_reducer=grad_reducer)
@@ -73,11 +74,17 @@ class GANTrainer:
         self.adversarial_loss = M.BCELoss()
         self.grad_reducer, self.world_size = grad_reducer, world_size
         self._bce_scale = {}
+        # independent networks of a sub-step on concurrent streams (functional._Lanes); the loop bodies are unchanged
+        self.overlap = overlap
 
     def batch(self, data: Batch) -> Dict[str, torch.Tensor]:
         """The twelve sub-steps of one batch, in the reference's order (train_IEMOCAP.py:355-382).
         Returns the six surviving loss values as device scalars (later sub-steps overwrite earlier ones,
         as in the reference)."""
+        with GF.overlap_networks(self.overlap):
+            return self._batch(data)
+
+    def _batch(self, data: Batch) -> Dict[str, torch.Tensor]:
         n = self.nets
         real_text, real_visual, real_acoustic = data.text, data.visual, data.acoustic
         seq_len, batch_size = real_text.size(0), real_text.size(1)
@@ -109,14 +116,19 @@ class GANTrainer:
 class ClassifierTrainer:
     """Stage 2 (reference ``train_or_eval_model``, train_IEMOCAP.py:103-197) for ``GAN_FFN``."""
 
-    def __init__(self, model: M.GAN_FFN, loss_weights=None, lr=FFN_LR, l2=FFN_L2, grad_reducer=None):
+    def __init__(self, model: M.GAN_FFN, loss_weights=None, lr=FFN_LR, l2=FFN_L2, grad_reducer=None, overlap: bool = True):
         self.model = model
+        self.overlap = overlap
         self.loss_function = M.MaskedNLLLoss(loss_weights)
         self.optimizer = FusedAdam(model, lr=lr, weight_decay=l2, grad_reducer=grad_reducer)
         self.grad_reducer = grad_reducer
 
     def step(self, data: Batch, train: bool = True):
         """One batch of the loop body (train_IEMOCAP.py:127-170).  Returns (loss, pred_, labels_)."""
+        with GF.overlap_networks(self.overlap):
+            return self._step(data, train)
+
+    def _step(self, data: Batch, train: bool = True):
         model, optimizer = self.model, self.optimizer
         model.train() if train else model.eval()
         if train:
