@@ -4,11 +4,12 @@ Drop-in for the hot-path classes of the reference's ``model.py`` (same names, co
 ``forward`` signatures and ``state_dict`` keys); every number is computed by the hand-written
 CUDA kernels in ``libganffn.so`` (C ABI: ``include/ganffn.h``).  There is no CPU fallback.
 """
-from .model import (AcousticDiscriminator, AcousticGenerator, BCELoss, GAN_FFN, MaskedNLLLoss, PositionalEncoding,
+from .model import (AcousticDiscriminator, AcousticGenerator, BCELoss, GAN_FFN, GAN_FFN_DialogueRNN, MaskedNLLLoss,
+                    PositionalEncoding,
                     TextDiscriminator, TextGenerator, VisualDiscriminator, VisualGenerator)
 from .optim import FusedAdam
 from .functional import manual_seed
 
 __all__ = ["AcousticGenerator", "VisualGenerator", "TextGenerator", "AcousticDiscriminator", "VisualDiscriminator",
-           "TextDiscriminator", "GAN_FFN", "MaskedNLLLoss", "BCELoss", "PositionalEncoding", "FusedAdam",
+           "TextDiscriminator", "GAN_FFN", "GAN_FFN_DialogueRNN", "MaskedNLLLoss", "BCELoss", "PositionalEncoding", "FusedAdam",
            "manual_seed"]

@@ -312,11 +312,21 @@ __device__ __forceinline__ void epi_vec(const TcParams& p, uint32_t stage, int m
     dscale = 1.0f / (1.0f - ep.p_drop);
   }
   const float dact_scale = ep.dact_scale;
-#pragma unroll 2
+  // all eight row groups of the residual / activation source are requested up front: one memory latency per
+  // sub-tile instead of one per row group (the dH = dZ W2 product reads 24.6 MB of h here)
+  float4 aux[8];
+  if (RES || DNZ) {
+#pragma unroll
+    for (int i8 = 0; i8 < 8; ++i8) {
+      aux[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * i8 < rows_left) aux[i8] = *reinterpret_cast<const float4*>(aptr + (size_t)i8 * astep);
+    }
+  }
+#pragma unroll
   for (int i8 = 0; i8 < 8; ++i8) {
     if (rows_left > 0) {
       float4 aux4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (RES || DNZ) aux4 = *reinterpret_cast<const float4*>(aptr);
+      if (RES || DNZ) aux4 = aux[i8];
       const float4 a4 = lds128(sptr);
       float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
       if (RELU) {
@@ -343,7 +353,6 @@ __device__ __forceinline__ void epi_vec(const TcParams& p, uint32_t stage, int m
       *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
     }
     cptr += cstep;
-    if (RES || DNZ) aptr += astep;
     sptr += 4 * 36 * 4;
     rows_left -= 4;
     if (DROP) z += zstep;

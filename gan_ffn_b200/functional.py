@@ -114,7 +114,10 @@ _scratch: Dict[Tuple[str, int], torch.Tensor] = {}
 
 def _scratch_tag(device: torch.device) -> str:
     """One workspace per stream: networks on different lanes run concurrently."""
-    return "main" if not _lanes.active else f"s{torch.cuda.current_stream(device).cuda_stream}"
+    if not _lanes.streams:
+        return "main"
+    h = torch.cuda.current_stream(device).cuda_stream
+    return f"s{h}" if _lanes.is_lane(h) else "main"
 
 
 def scratch(device: torch.device, floats: int, tag: str = "main") -> torch.Tensor:
@@ -166,6 +169,9 @@ class _Lanes:
         k = self.counter % self.n
         self.counter += 1
         return k, pool[k]
+
+    def is_lane(self, handle: int) -> bool:
+        return any(st.cuda_stream == handle for pool in self.streams.values() for st in pool)
 
     def touch(self, stream: torch.cuda.Stream) -> None:
         self.busy[stream.cuda_stream] = stream
@@ -314,8 +320,8 @@ class _NetFunction(torch.autograd.Function):
         ws = scratch(x.device, L.query("ganffn_net_scratch_floats", *dims), _scratch_tag(x.device))
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         cur = torch.cuda.current_stream(x.device)
-        if _lanes.active:
-            _lanes.touch(cur)
+        if _lanes.streams and _lanes.is_lane(cur.cuda_stream):
+            _lanes.touch(cur)   # a backward pass on a lane (autograd runs it where the forward ran): join before use
         if not arena.grads_live():
             # Parameter gradients are accumulated by the kernels (red.global.add from the wgrad GEMMs and the
             # LayerNorm backward), torch-style: a fresh backward starts from a zeroed arena (one memset) -- done

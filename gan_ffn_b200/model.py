@@ -230,6 +230,42 @@ class GAN_FFN(nn.Module):
         return log_prob, alpha, alpha_f, alpha_b
 
 
+class GAN_FFN_DialogueRNN(nn.Module):
+    """reference model.py:1465-1528: the same three generators and sum as ``GAN_FFN`` (the part on the sm_100a
+    kernels), feeding the DialogueRNN ``BiModel`` head (stock PyTorch, ``dialogue_rnn.py``).  ``fc1`` is constructed
+    and unused, as in the reference.  ``forward(acoustic, visual, text, qmask, umask)`` returns
+    ``(log_prob, alpha, alpha_f, alpha_b)``."""
+
+    def __init__(self, acoustic_generator, visual_generator, text_generator, D_m, D_g, D_p, D_e, D_h, D_a, n_classes,
+                 listener_state, context_attention, dropout_rec, dropout):
+        super(GAN_FFN_DialogueRNN, self).__init__()
+        from .dialogue_rnn import BiModel
+        self.n_classes = n_classes
+        self.acoustic_generator = acoustic_generator
+        self.visual_generator = visual_generator
+        self.text_generator = text_generator
+        self.gelu = nn.GELU()
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.bi_model = BiModel(D_m=D_m, D_g=D_g, D_p=D_p, D_e=D_e, D_h=D_h, n_classes=n_classes,
+                                listener_state=listener_state, context_attention=context_attention, D_a=D_a,
+                                dropout_rec=dropout_rec, dropout=dropout)
+        self.fc1 = nn.Linear(100, n_classes)
+
+    def fusion(self, acoustic, visual, text):
+        """The fused features the head consumes (model.py:1517-1524)."""
+        acoustic_fusion = self.acoustic_generator(acoustic)
+        visual_fusion = self.visual_generator(visual)
+        text_fusion = self.text_generator(text)
+        GF.join_lanes()   # the sum below is a plain torch op on the caller's stream
+        return acoustic_fusion + visual_fusion + text_fusion
+
+    def forward(self, acoustic, visual, text, qmask, umask):
+        fusion = self.fusion(acoustic, visual, text)
+        log_prob, alpha, alpha_f, alpha_b = self.bi_model(fusion, qmask, umask)
+        return log_prob, alpha, alpha_f, alpha_b
+
+
 class MaskedNLLLoss(nn.Module):
     """reference model.py:62-81.  ``den_override`` (> 0) replaces the denominator
     sum(w[target]*mask) -- used under dialogue sharding, where it must be the *global* sum."""
