@@ -1,0 +1,350 @@
+// Dialogue-graph kernels (north_star parts 2-3): window-graph construction straight into CSR and segmented,
+// atomic-free gather / scatter-add for the relation-typed and plain graph convolutions.
+//
+// ABSENT FROM THE REFERENCE: the semantics are this library's own, stated in include/ganffn.h
+// and pinned by oracle/graph_oracle.py ("parity unpinned -- no reference implementation").
+//
+// All of this is HBM-bound integer / gather work (no tensor cores): the design rules are coalescing and grid size.
+//   * build: one warp per dialogue.  Lane = target utterance; its degree is a closed form of (t, len, wp, wf), a
+//     warp scan gives the row offsets, and each lane writes its (<= wp+wf+1) edges contiguously.  Rows of one
+//     dialogue are adjacent, so a warp's stores cover one contiguous span of col / etype / edge_index.
+//   * gather: one warp per node.  Lane c owns one float4 of the feature row, so every neighbour row is one coalesced
+//     400-byte (d=100) read; neighbour rows are re-read by <= wp+wf+1 nodes of the same dialogue, i.e. from L2.
+//     The backward "scatter-add" runs on the transposed CSR as the same gather: no atomics, deterministic.
+#include "kernels.h"
+
+namespace ganffn {
+namespace {
+
+__device__ __forceinline__ int rel_id(int spk_src, int spk_dst, bool past, int n_spk) {
+  return ((spk_src * n_spk + spk_dst) << 1) | (past ? 0 : 1);
+}
+
+__device__ __forceinline__ int64_t window_edges(int L, int wp, int wf) {
+  int64_t e = 0;
+  for (int i = 0; i < L; ++i) e += min(L - 1, i + wf) - max(0, i - wp) + 1;
+  return e;
+}
+
+// One block: exclusive scans of the per-dialogue node and edge counts (B is at most a few 10^4).
+__global__ void __launch_bounds__(1024) graph_offsets_kernel(const int* __restrict__ lengths, int B, int wp, int wf,
+                                                             int64_t* __restrict__ node_off, int64_t* __restrict__ edge_off) {
+  __shared__ int64_t sn[1024], se[1024];
+  __shared__ int64_t carry_n, carry_e;
+  const int t = threadIdx.x;
+  if (t == 0) { carry_n = 0; carry_e = 0; }
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int b = base + t;
+    const int L = b < B ? lengths[b] : 0;
+    sn[t] = L;
+    se[t] = b < B ? window_edges(L, wp, wf) : 0;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+      const int64_t a = t >= o ? sn[t - o] : 0, c = t >= o ? se[t - o] : 0;
+      __syncthreads();
+      sn[t] += a; se[t] += c;
+      __syncthreads();
+    }
+    if (b < B) {
+      node_off[b] = carry_n + sn[t] - L;
+      edge_off[b] = carry_e + se[t] - window_edges(L, wp, wf);
+    }
+    __syncthreads();
+    if (t == 1023) { carry_n += sn[1023]; carry_e += se[1023]; }
+    __syncthreads();
+  }
+  if (t == 0) { node_off[B] = carry_n; edge_off[B] = carry_e; }
+}
+
+// Warp per dialogue.  Rows = targets with window [i-wp, i+wf] (transposed: rows = sources with window [j-wf, j+wp]).
+__global__ void __launch_bounds__(256) graph_build_kernel(const int* __restrict__ lengths, const int* __restrict__ spk,
+                                                          const int64_t* __restrict__ node_off,
+                                                          const int64_t* __restrict__ edge_off, int B, int wp, int wf,
+                                                          int n_spk, int transposed, int64_t* __restrict__ rowptr,
+                                                          int* __restrict__ col, int* __restrict__ etype,
+                                                          int64_t* __restrict__ edge_index, int64_t E,
+                                                          int* __restrict__ node_b, int* __restrict__ node_t,
+                                                          float* __restrict__ inv_cnt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int b = warp;
+  const int L = lengths[b];
+  const int64_t n0 = node_off[b], e0 = edge_off[b];
+  const int back = transposed ? wf : wp, fwd = transposed ? wp : wf;   // window of a row: [r - back, r + fwd]
+  const int R = 2 * n_spk * n_spk;
+  int64_t carry = 0;
+  for (int base = 0; base < L; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < L;
+    const int lo = max(0, i - back), hi = min(L - 1, i + fwd);
+    const int deg = valid ? hi - lo + 1 : 0;
+    int incl = deg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (valid) {
+      const int64_t row = n0 + i;
+      const int64_t e_row = e0 + carry + (incl - deg);
+      rowptr[row] = e_row;
+      const int si = spk[row];
+      if (node_b) { node_b[row] = b; node_t[row] = i; }
+      float* cnt = inv_cnt ? inv_cnt + row * R : nullptr;     // this thread owns the row: plain read-modify-write
+      if (cnt)
+        for (int r = 0; r < R; ++r) cnt[r] = 0.f;
+      for (int j = lo; j <= hi; ++j) {
+        const int64_t e = e_row + (j - lo);
+        const int sj = spk[n0 + j];
+        // row = target i, entry = source j (transposed: row = source, entry = target): the relation is always
+        // (speaker of the source, speaker of the target, source before target)
+        const int r = transposed ? rel_id(si, sj, i < j, n_spk) : rel_id(sj, si, j < i, n_spk);
+        col[e] = (int)(n0 + j);
+        etype[e] = r;
+        if (edge_index) { edge_index[e] = transposed ? row : n0 + j; edge_index[E + e] = transposed ? n0 + j : row; }
+        if (cnt) cnt[r] += 1.f;
+      }
+      if (cnt)
+        for (int r = 0; r < R; ++r) cnt[r] = cnt[r] > 0.f ? 1.f / cnt[r] : 0.f;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) rowptr[n0 + L] = e0 + carry;   // the next dialogue's first row writes the same value
+}
+
+__global__ void __launch_bounds__(256) graph_pack_kernel(const float* __restrict__ x, const int* __restrict__ node_b,
+                                                         const int* __restrict__ node_t, float* __restrict__ out,
+                                                         int64_t N, int B, int d4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * d4) return;
+  const int64_t n = idx / d4;
+  const int c = (int)(idx % d4);
+  const float4* src = reinterpret_cast<const float4*>(x) + ((int64_t)node_t[n] * B + node_b[n]) * d4 + c;
+  reinterpret_cast<float4*>(out)[idx] = __ldg(src);
+}
+
+__global__ void __launch_bounds__(256) graph_unpack_kernel(const float* __restrict__ xn, const int* __restrict__ lengths,
+                                                           const int64_t* __restrict__ node_off, float* __restrict__ out,
+                                                           int S, int B, int d4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)S * B * d4) return;
+  const int c = (int)(idx % d4);
+  const int64_t tb = idx / d4;
+  const int b = (int)(tb % B), t = (int)(tb / B);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < lengths[b]) v = __ldg(reinterpret_cast<const float4*>(xn) + (node_off[b] + t) * d4 + c);
+  reinterpret_cast<float4*>(out)[idx] = v;
+}
+
+constexpr int GV = 4;   // float4 per lane: d <= 512
+
+__device__ __forceinline__ void add4(float4& a, const float4 v, float w) {
+  a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+}
+
+// Warp per node; relation-outer, edge-inner: out[n, r, :] = inv[n, r] * sum_{e: etype = r} x[col[e], :].
+__global__ void __launch_bounds__(256) graph_gather_typed_kernel(const float* __restrict__ x, const int64_t* __restrict__ rowptr,
+                                                                 const int* __restrict__ col, const int* __restrict__ etype,
+                                                                 const float* __restrict__ inv_cnt, float* __restrict__ out,
+                                                                 int64_t N, int R, int d4) {
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int64_t beg = rowptr[n], end = rowptr[n + 1];
+  const float4* xv = reinterpret_cast<const float4*>(x);
+  float4* ov = reinterpret_cast<float4*>(out) + n * R * d4;
+  // first (usually only) chunk of <= 32 edges lives in registers: lane e holds (col, etype) of edge beg + e
+  const int deg0 = (int)((end - beg) < 32 ? (end - beg) : 32);
+  const int c0 = lane < deg0 ? col[beg + lane] : 0;
+  const int t0 = lane < deg0 ? etype[beg + lane] : -1;
+  for (int r = 0; r < R; ++r) {
+    float4 acc[GV];
+#pragma unroll
+    for (int k = 0; k < GV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned m = __ballot_sync(0xffffffffu, t0 == r);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t j = __shfl_sync(0xffffffffu, c0, src);
+#pragma unroll
+      for (int k = 0; k < GV; ++k) {
+        const int c = lane + 32 * k;
+        if (c < d4) add4(acc[k], __ldg(xv + j * d4 + c), 1.f);
+      }
+    }
+    for (int64_t e = beg + 32; e < end; ++e) {   // windows wider than 32 edges (not the DialogueGCN defaults)
+      if (etype[e] == r) {
+        const int64_t j = col[e];
+#pragma unroll
+        for (int k = 0; k < GV; ++k) {
+          const int c = lane + 32 * k;
+          if (c < d4) add4(acc[k], __ldg(xv + j * d4 + c), 1.f);
+        }
+      }
+    }
+    const float w = inv_cnt[n * R + r];
+#pragma unroll
+    for (int k = 0; k < GV; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d4) ov[(int64_t)r * d4 + c] = make_float4(acc[k].x * w, acc[k].y * w, acc[k].z * w, acc[k].w * w);
+    }
+  }
+}
+
+// Warp per node: out[n, :] = sum_e w_e * in[col[e], slot_e, :].
+template <bool TYPED, bool WEIGHTED>
+__global__ void __launch_bounds__(256) graph_gather_sum_kernel(const float* __restrict__ in, const int64_t* __restrict__ rowptr,
+                                                               const int* __restrict__ col, const int* __restrict__ etype,
+                                                               const float* __restrict__ inv_cnt, float* __restrict__ out,
+                                                               int64_t N, int in_slots, int R, int d4) {
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int64_t beg = rowptr[n], end = rowptr[n + 1];
+  const float4* iv = reinterpret_cast<const float4*>(in);
+  float4 acc[GV];
+#pragma unroll
+  for (int k = 0; k < GV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t cb = beg; cb < end; cb += 32) {
+    const int cnt = (int)((end - cb) < 32 ? (end - cb) : 32);
+    const int cj = lane < cnt ? col[cb + lane] : 0;
+    const int tj = (TYPED || WEIGHTED) && lane < cnt ? etype[cb + lane] : 0;
+    const float wj = WEIGHTED && lane < cnt ? __ldg(inv_cnt + (int64_t)cj * R + tj) : 1.f;
+    for (int s = 0; s < cnt; ++s) {
+      const int64_t j = __shfl_sync(0xffffffffu, cj, s);
+      const int slot = TYPED ? __shfl_sync(0xffffffffu, tj, s) : 0;
+      const float w = WEIGHTED ? __shfl_sync(0xffffffffu, wj, s) : 1.f;
+      const float4* row = iv + (j * in_slots + slot) * d4;
+#pragma unroll
+      for (int k = 0; k < GV; ++k) {
+        const int c = lane + 32 * k;
+        if (c < d4) add4(acc[k], __ldg(row + c), w);
+      }
+    }
+  }
+  float4* ov = reinterpret_cast<float4*>(out) + n * d4;
+#pragma unroll
+  for (int k = 0; k < GV; ++k) {
+    const int c = lane + 32 * k;
+    if (c < d4) ov[c] = acc[k];
+  }
+}
+
+}  // namespace
+
+int graph_offsets(const int* lengths, int B, int wp, int wf, int64_t* node_off, int64_t* edge_off, cudaStream_t st) {
+  GANFFN_CHECK_ARG(lengths && node_off && edge_off && B >= 1 && wp >= 0 && wf >= 0, "graph_offsets: bad arguments");
+  graph_offsets_kernel<<<1, 1024, 0, st>>>(lengths, B, wp, wf, node_off, edge_off);
+  GANFFN_LAUNCHED("graph_offsets_kernel");
+  return GANFFN_OK;
+}
+
+int graph_build(const int* lengths, const int* speakers, const int64_t* node_off, const int64_t* edge_off, int B, int wp,
+                int wf, int n_speakers, int transposed, int64_t* rowptr, int* col, int* etype, int64_t* edge_index,
+                int64_t n_edges, int* node_b, int* node_t, float* inv_cnt, cudaStream_t st) {
+  GANFFN_CHECK_ARG(lengths && speakers && node_off && edge_off && rowptr && col && etype, "graph_build: null pointer");
+  GANFFN_CHECK_ARG(B >= 1 && wp >= 0 && wf >= 0 && n_speakers >= 1 && n_speakers <= 16, "graph_build: bad arguments");
+  GANFFN_CHECK_ARG((node_b == nullptr) == (node_t == nullptr), "graph_build: node_b and node_t go together");
+  const int wpb = 8;
+  graph_build_kernel<<<cdiv(B, wpb), wpb * 32, 0, st>>>(lengths, speakers, node_off, edge_off, B, wp, wf, n_speakers,
+                                                        transposed, rowptr, col, etype, edge_index, n_edges, node_b, node_t,
+                                                        inv_cnt);
+  GANFFN_LAUNCHED("graph_build_kernel");
+  return GANFFN_OK;
+}
+
+int graph_pack(const float* x_sbd, const int* node_b, const int* node_t, float* x_nodes, int64_t N, int B, int d,
+               cudaStream_t st) {
+  GANFFN_CHECK_ARG(x_sbd && node_b && node_t && x_nodes && d % 4 == 0, "graph_pack: bad arguments (d must be a multiple of 4)");
+  if (N <= 0) return GANFFN_OK;
+  graph_pack_kernel<<<cdiv(N * (d / 4), 256), 256, 0, st>>>(x_sbd, node_b, node_t, x_nodes, N, B, d / 4);
+  GANFFN_LAUNCHED("graph_pack_kernel");
+  return GANFFN_OK;
+}
+
+int graph_unpack(const float* x_nodes, const int* lengths, const int64_t* node_off, float* x_sbd, int S, int B, int d,
+                 cudaStream_t st) {
+  GANFFN_CHECK_ARG(x_nodes && lengths && node_off && x_sbd && d % 4 == 0, "graph_unpack: bad arguments (d must be a multiple of 4)");
+  graph_unpack_kernel<<<cdiv((int64_t)S * B * (d / 4), 256), 256, 0, st>>>(x_nodes, lengths, node_off, x_sbd, S, B, d / 4);
+  GANFFN_LAUNCHED("graph_unpack_kernel");
+  return GANFFN_OK;
+}
+
+int graph_gather_typed(const float* x, const int64_t* rowptr, const int* col, const int* etype, const float* inv_cnt,
+                       float* out, int64_t N, int R, int d, cudaStream_t st) {
+  GANFFN_CHECK_ARG(x && rowptr && col && etype && inv_cnt && out, "graph_gather_typed: null pointer");
+  GANFFN_CHECK_ARG(d % 4 == 0 && d <= 128 * GV && R >= 1, "graph_gather_typed: d=%d must be a multiple of 4 and <= %d", d, 128 * GV);
+  if (N <= 0) return GANFFN_OK;
+  graph_gather_typed_kernel<<<cdiv(N, 8), 256, 0, st>>>(x, rowptr, col, etype, inv_cnt, out, N, R, d / 4);
+  GANFFN_LAUNCHED("graph_gather_typed_kernel");
+  return GANFFN_OK;
+}
+
+int graph_gather_sum(const float* in, const int64_t* rowptr, const int* col, const int* etype, const float* inv_cnt,
+                     float* out, int64_t N, int in_slots, int R, int d, cudaStream_t st) {
+  GANFFN_CHECK_ARG(in && rowptr && col && out, "graph_gather_sum: null pointer");
+  GANFFN_CHECK_ARG(d % 4 == 0 && d <= 128 * GV && in_slots >= 1, "graph_gather_sum: d=%d must be a multiple of 4 and <= %d", d, 128 * GV);
+  GANFFN_CHECK_ARG((in_slots == 1 && inv_cnt == nullptr) || etype != nullptr, "graph_gather_sum: typed / weighted gathers need etype");
+  if (N <= 0) return GANFFN_OK;
+  const dim3 grid(cdiv(N, 8));
+  const bool typed = in_slots > 1, weighted = inv_cnt != nullptr;
+  if (typed && weighted) graph_gather_sum_kernel<true, true><<<grid, 256, 0, st>>>(in, rowptr, col, etype, inv_cnt, out, N, in_slots, R, d / 4);
+  else if (typed) graph_gather_sum_kernel<true, false><<<grid, 256, 0, st>>>(in, rowptr, col, etype, inv_cnt, out, N, in_slots, R, d / 4);
+  else if (weighted) graph_gather_sum_kernel<false, true><<<grid, 256, 0, st>>>(in, rowptr, col, etype, inv_cnt, out, N, in_slots, R, d / 4);
+  else graph_gather_sum_kernel<false, false><<<grid, 256, 0, st>>>(in, rowptr, col, etype, inv_cnt, out, N, in_slots, R, d / 4);
+  GANFFN_LAUNCHED("graph_gather_sum_kernel");
+  return GANFFN_OK;
+}
+
+}  // namespace ganffn
+
+using namespace ganffn;
+static inline cudaStream_t GS(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int64_t ganffn_graph_num_edges_host(const int* lengths_host, int n_dialogues, int wp, int wf, int64_t* n_nodes) {
+  int64_t E = 0, N = 0;
+  for (int b = 0; b < n_dialogues; ++b) {
+    const int L = lengths_host[b];
+    N += L;
+    for (int i = 0; i < L; ++i) E += std::min(L - 1, i + wf) - std::max(0, i - wp) + 1;
+  }
+  if (n_nodes) *n_nodes = N;
+  return E;
+}
+
+int ganffn_graph_offsets(const int* lengths, int n_dialogues, int wp, int wf, int64_t* node_off, int64_t* edge_off,
+                         void* stream) {
+  return graph_offsets(lengths, n_dialogues, wp, wf, node_off, edge_off, GS(stream));
+}
+
+int ganffn_graph_build(const int* lengths, const int* speakers, const int64_t* node_off, const int64_t* edge_off,
+                       int n_dialogues, int wp, int wf, int n_speakers, int transposed, int64_t* rowptr, int* col, int* etype,
+                       int64_t* edge_index, int64_t n_edges, int* node_b, int* node_t, float* inv_cnt, void* stream) {
+  return graph_build(lengths, speakers, node_off, edge_off, n_dialogues, wp, wf, n_speakers, transposed, rowptr, col, etype,
+                     edge_index, n_edges, node_b, node_t, inv_cnt, GS(stream));
+}
+
+int ganffn_graph_pack(const float* x_sbd, const int* node_b, const int* node_t, float* x_nodes, int64_t n_nodes, int B, int d,
+                      void* stream) {
+  return graph_pack(x_sbd, node_b, node_t, x_nodes, n_nodes, B, d, GS(stream));
+}
+
+int ganffn_graph_unpack(const float* x_nodes, const int* lengths, const int64_t* node_off, float* x_sbd, int S, int B, int d,
+                        void* stream) {
+  return graph_unpack(x_nodes, lengths, node_off, x_sbd, S, B, d, GS(stream));
+}
+
+int ganffn_graph_gather_typed(const float* x, const int64_t* rowptr, const int* col, const int* etype, const float* inv_cnt,
+                              float* out, int64_t n_nodes, int n_rel, int d, void* stream) {
+  return graph_gather_typed(x, rowptr, col, etype, inv_cnt, out, n_nodes, n_rel, d, GS(stream));
+}
+
+int ganffn_graph_gather_sum(const float* in, const int64_t* rowptr, const int* col, const int* etype, const float* inv_cnt,
+                            float* out, int64_t n_nodes, int in_slots, int n_rel, int d, void* stream) {
+  return graph_gather_sum(in, rowptr, col, etype, inv_cnt, out, n_nodes, in_slots, n_rel, d, GS(stream));
+}
+
+}  // extern "C"

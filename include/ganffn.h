@@ -208,6 +208,48 @@ int64_t ganffn_net_stash_floats(int kind, int S, int B, int d_in, int d, int nhe
 int64_t ganffn_net_scratch_floats(int kind, int S, int B, int d_in, int d, int nhead, int dff,
                                   int nlayers, int h1, int h2);
 
+/* ---- dialogue graph (north_star parts 2-3) --------------------------------------------------------------------
+ * ABSENT FROM THE REFERENCE: /root/reference has no edge construction and no graph
+ * convolution, so there is nothing to be bit-exact against ("parity unpinned -- no reference implementation").
+ * The semantics below are this library's own (DialogueGCN-style window graph), pinned by oracle/graph_oracle.py:
+ *   - nodes: the real utterances, dialogue-major: node(b, t) = node_off[b] + t, t < lengths[b];
+ *   - edges: for every target i of a dialogue, one edge from every source j with i - wp <= j <= i + wf (self
+ *     loop included), stored as CSR over targets with sources ascending -- this is the canonical edge order, and
+ *     edge_index[0][e] = source, edge_index[1][e] = target in that order;
+ *   - edge_type[e] = ((speaker[j] * n_speakers + speaker[i]) << 1) | (j < i ? 0 : 1)   (2 * n_speakers^2 relations);
+ *   - the transposed structure (CSR over sources: targets i with j - wf <= i <= j + wp, ascending) makes the
+ *     backward scatter-add a segmented gather as well: no atomics anywhere.
+ * lengths [B] and speakers [N] are int32 device arrays; offsets are int64; col / etype are int32. */
+int64_t ganffn_graph_num_edges_host(const int* lengths_host, int n_dialogues, int wp, int wf, int64_t* n_nodes);
+/* node_off[B+1], edge_off[B+1] (exclusive scans; one thread block). */
+int ganffn_graph_offsets(const int* lengths, int n_dialogues, int wp, int wf, int64_t* node_off,
+                         int64_t* edge_off, void* stream);
+/* Warp per dialogue, straight into CSR.  transposed = 0: rows are targets (rowptr/col/etype as above; node_b /
+ * node_t [N] and inv_cnt [N, n_rel] = 1 / #edges of that relation into the node (0 if none) are written when not
+ * null; edge_index [2, E] int64 optional).  transposed = 1: rows are sources, col = targets, same etype. */
+int ganffn_graph_build(const int* lengths, const int* speakers, const int64_t* node_off,
+                       const int64_t* edge_off, int n_dialogues, int wp, int wf, int n_speakers,
+                       int transposed, int64_t* rowptr, int* col, int* etype, int64_t* edge_index,
+                       int64_t n_edges, int* node_b, int* node_t, float* inv_cnt, void* stream);
+/* (S,B,d) zero-padded batch <-> packed [N,d] node features (and the same pair for gradients). */
+int ganffn_graph_pack(const float* x_sbd, const int* node_b, const int* node_t, float* x_nodes,
+                      int64_t n_nodes, int B, int d, void* stream);
+int ganffn_graph_unpack(const float* x_nodes, const int* lengths, const int64_t* node_off, float* x_sbd,
+                        int S, int B, int d, void* stream);
+/* Relation-typed mean aggregation: out[n, r, :] = inv_cnt[n, r] * sum_{e in row n, etype[e] = r} x[col[e], :].
+ * out is [N, n_rel, d] (empty relations are written as zeros): the dense contraction with the relation weights is
+ * then one GEMM of [N, n_rel*d] x [n_rel*d, h] (ganffn_linear_fwd). */
+int ganffn_graph_gather_typed(const float* x, const int64_t* rowptr, const int* col, const int* etype,
+                              const float* inv_cnt, float* out, int64_t n_nodes, int n_rel, int d,
+                              void* stream);
+/* Plain segmented gather-sum: out[n, :] = sum_{e in row n} w_e * in[col[e], slot_e, :], in is [N, in_slots, d];
+ * slot_e = etype[e] when in_slots > 1 else 0; w_e = inv_cnt[col[e], etype[e]] when inv_cnt != NULL else 1.
+ * Serves GraphConv forward (CSR), GraphConv backward (transposed CSR) and the backward of
+ * ganffn_graph_gather_typed (transposed CSR, in = d_out [N, n_rel, d], weights = inv_cnt). */
+int ganffn_graph_gather_sum(const float* in, const int64_t* rowptr, const int* col, const int* etype,
+                            const float* inv_cnt, float* out, int64_t n_nodes, int in_slots, int n_rel,
+                            int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
