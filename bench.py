@@ -294,6 +294,18 @@ def run_ours(args):
                 "gemm_share_of_step": gemm_ms / (ms_total / args.steps) if ms_total else None,
                 "note": "fp32-parity arithmetic: FFMA tiles or 3xTF32 tcgen05 (3 MMAs per product at half the bf16 rate), so frac <= ~0.17 by construction against the bf16 peak"}
 
+    # ---- dialogue-graph kernels (north_star parts 2-3; no reference implementation): achieved HBM GB/s -------------
+    graph = None
+    if rank == 0 and world == 1 and not args.no_graph:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import graph_bench
+            del flush
+            torch.cuda.empty_cache()
+            graph = graph_bench.graph_leg(utterances=args.graph_utterances, reps=3, device=dev)
+        except Exception as exc:   # the headline must not depend on the auxiliary leg
+            graph = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -315,6 +327,8 @@ def run_ours(args):
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if graph is not None:
+            line["graph"] = graph
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -332,6 +346,8 @@ def main():
     ap.add_argument("--ref-dialogues", type=int, default=0, help="dialogues per step of the CPU reference arm (0 = fit ~4 min)")
     ap.add_argument("--engine", default=None, choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the dialogue-graph kernel leg (HBM GB/s of edge build / gathers)")
+    ap.add_argument("--graph-utterances", type=int, default=1_000_000)
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -170,9 +170,9 @@ class _GraphLayer(torch.autograd.Function):
         st = GF._stream(x)
         if typed:
             L.call("ganffn_graph_gather_typed", ptr(x), ptr(g.rowptr), ptr(g.col), ptr(g.etype), ptr(g.inv_cnt), ptr(agg), N,
-                   g.n_rel, d, st)
+                   g.n_rel, d, ptr(g.node_off), g.B, g.S, st)
         else:
-            L.call("ganffn_graph_gather_sum", ptr(x), ptr(g.rowptr), ptr(g.col), None, None, ptr(agg), N, 1, g.n_rel, d, st)
+            L.call("ganffn_graph_gather_sum", ptr(x), ptr(g.rowptr), ptr(g.col), None, None, ptr(agg), N, 1, g.n_rel, d, ptr(g.node_off), g.B, g.S, st)
         y0 = _linear_fwd(x, w_root, bias)
         y = _linear_fwd(agg, w_rel, None, residual=y0)
         ctx.save_for_backward(x, agg, w_rel, w_root)
@@ -192,9 +192,9 @@ class _GraphLayer(torch.autograd.Function):
         st = GF._stream(dy)
         if typed:
             L.call("ganffn_graph_gather_sum", ptr(dagg), ptr(g.rowptr_t), ptr(g.col_t), ptr(g.etype_t), ptr(g.inv_cnt), ptr(dmsg),
-                   N, g.n_rel, g.n_rel, d, st)
+                   N, g.n_rel, g.n_rel, d, None, 0, 0, st)
         else:
-            L.call("ganffn_graph_gather_sum", ptr(dagg), ptr(g.rowptr_t), ptr(g.col_t), None, None, ptr(dmsg), N, 1, g.n_rel, d, st)
+            L.call("ganffn_graph_gather_sum", ptr(dagg), ptr(g.rowptr_t), ptr(g.col_t), None, None, ptr(dmsg), N, 1, g.n_rel, d, ptr(g.node_off), g.B, g.S, st)
         dx = _linear_dgrad(dy, w_root, d, residual=dmsg)
         dw_rel, _ = _linear_wgrad(dy, agg, False)
         dw_root, db = _linear_wgrad(dy, x, True)

@@ -238,17 +238,19 @@ int ganffn_graph_unpack(const float* x_nodes, const int* lengths, const int64_t*
                         int S, int B, int d, void* stream);
 /* Relation-typed mean aggregation: out[n, r, :] = inv_cnt[n, r] * sum_{e in row n, etype[e] = r} x[col[e], :].
  * out is [N, n_rel, d] (empty relations are written as zeros): the dense contraction with the relation weights is
- * then one GEMM of [N, n_rel*d] x [n_rel*d, h] (ganffn_linear_fwd). */
+ * then one GEMM of [N, n_rel*d] x [n_rel*d, h] (ganffn_linear_fwd).
+ * node_off [B+1] / n_dialogues / max_len (optional: NULL, 0, 0): when given and a dialogue's rows fit in shared
+ * memory, one CTA stages one dialogue and HBM sees every input row once (otherwise rows are re-read from L2). */
 int ganffn_graph_gather_typed(const float* x, const int64_t* rowptr, const int* col, const int* etype,
                               const float* inv_cnt, float* out, int64_t n_nodes, int n_rel, int d,
-                              void* stream);
+                              const int64_t* node_off, int n_dialogues, int max_len, void* stream);
 /* Plain segmented gather-sum: out[n, :] = sum_{e in row n} w_e * in[col[e], slot_e, :], in is [N, in_slots, d];
  * slot_e = etype[e] when in_slots > 1 else 0; w_e = inv_cnt[col[e], etype[e]] when inv_cnt != NULL else 1.
  * Serves GraphConv forward (CSR), GraphConv backward (transposed CSR) and the backward of
  * ganffn_graph_gather_typed (transposed CSR, in = d_out [N, n_rel, d], weights = inv_cnt). */
 int ganffn_graph_gather_sum(const float* in, const int64_t* rowptr, const int* col, const int* etype,
                             const float* inv_cnt, float* out, int64_t n_nodes, int in_slots, int n_rel,
-                            int d, void* stream);
+                            int d, const int64_t* node_off, int n_dialogues, int max_len, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Achieved HBM GB/s of the dialogue-graph kernels (north_star: ">= 50% of HBM roofline on the ... scatter kernels").
+Standalone (`python tools/graph_bench.py`) or imported by bench.py (`graph_leg`).  Sweep-shaped problem: dialogues of
+10..110 turns, window 10/10, two speakers, d = 100 features; algorithmic bytes per kernel are stated next to each
+number.  CUDA events on the launching stream, L2 flushed (256 MiB write) before every timed launch."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+
+def graph_leg(utterances=1_000_000, d=100, wp=10, wf=10, reps=5, device="cuda"):
+    from gan_ffn_b200 import synthetic
+    from gan_ffn_b200._lib import lib, ptr
+    from gan_ffn_b200.graph import DialogueGraph
+    L = lib()
+    dev = torch.device(device)
+    n_dialogues = int(round(utterances / 60))
+    lengths = synthetic.ragged_lengths(n_dialogues, 10, 110, seed=11)
+    S, B = max(lengths), n_dialogues
+    spk = torch.randint(0, 2, (S, B), device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def timed(fn):
+        ms = []
+        for _ in range(reps + 1):
+            flush.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(e))
+        return sorted(ms[1:])[len(ms[1:]) // 2]
+
+    g = DialogueGraph(lengths, spk, wp, wf, 2, device=dev)
+    N, E, R = g.N, g.E, g.n_rel
+    x = torch.rand(N, d, device=dev)
+    agg = torch.empty(N, R * d, device=dev)
+    dx = torch.empty(N, d, device=dev)
+    out = {}
+
+    def build():
+        L.call("ganffn_graph_build", ptr(g.lengths), ptr(g.speakers), ptr(g.node_off), ptr(g.edge_off), g.B, wp, wf, 2, 0,
+               ptr(g.rowptr), ptr(g.col), ptr(g.etype), ptr(g.edge_index), E, ptr(g.node_b), ptr(g.node_t), ptr(g.inv_cnt), st)
+    ms = timed(build)
+    by = E * (4 + 4 + 16) + N * (8 + 4 + 4 + 4 * R + 4) + 4 * B * 5     # col, etype, edge_index | rowptr, node_b/t, inv_cnt, speakers
+    out["edge_build"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6, "edges_per_s": E / ms * 1e3}
+
+    def typed():
+        L.call("ganffn_graph_gather_typed", ptr(x), ptr(g.rowptr), ptr(g.col), ptr(g.etype), ptr(g.inv_cnt), ptr(agg), N, R, d, ptr(g.node_off), g.B, g.S, st)
+    ms = timed(typed)
+    by = N * d * 4 + E * 8 + N * 8 + N * R * 4 + N * R * d * 4            # x once, CSR, inv_cnt, out
+    out["rgcn_gather_fwd"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6}
+
+    def typed_bwd():
+        L.call("ganffn_graph_gather_sum", ptr(agg), ptr(g.rowptr_t), ptr(g.col_t), ptr(g.etype_t), ptr(g.inv_cnt), ptr(dx), N, R, R, d, None, 0, 0, st)
+    ms = timed(typed_bwd)
+    nnz = int((g.inv_cnt[:N * R] > 0).sum().item())                        # non-empty (target, relation) rows of d_out
+    by = nnz * d * 4 + E * 8 + N * 8 + N * R * 4 + N * d * 4               # every non-empty d_out row once, CSR, inv, dx
+    out["rgcn_gather_bwd"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6}
+
+    def plain():
+        L.call("ganffn_graph_gather_sum", ptr(x), ptr(g.rowptr), ptr(g.col), None, None, ptr(dx), N, 1, R, d, ptr(g.node_off), g.B, g.S, st)
+    ms = timed(plain)
+    by = N * d * 4 + E * 4 + N * 8 + N * d * 4                             # x once, CSR, out
+    out["graphconv_gather"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6500.0))
+    for v in out.values():
+        v["frac_of_hbm_peak"] = v["GBps"] / peak
+    return {"workload": f"{N} utterances in {B} dialogues of 10..110 turns, window {wp}/{wf}, 2 speakers, d={d}: {E} edges, {R} relations",
+            "hbm_peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6500 GB/s",
+            "parity": "unpinned: no reference implementation (SURVEY.md D1/D2); checked against oracle/graph_oracle.py",
+            "kernels": out}
+
+
+if __name__ == "__main__":
+    print(json.dumps(graph_leg()), flush=True)
