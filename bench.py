@@ -331,8 +331,18 @@ def run_ours(args):
             line["graph"] = graph
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The replayed graphs hold the recorded NCCL kernels: release them, drain the device, then leave without tearing
+        # the communicator down (ncclCommDestroy under live captured collectives can wait forever; the processes
+        # exit right after, which releases everything).
+        stepper._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

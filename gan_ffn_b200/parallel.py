@@ -69,6 +69,15 @@ class GradReducer:
         dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
         return float(den.item())
 
+    def global_nll_denominator_tensor(self, label: torch.Tensor, umask: torch.Tensor, weight: Optional[torch.Tensor]) -> torch.Tensor:
+        """The same sum as a device scalar, never read on the host: the all-reduce and everything after it can be
+        recorded into a CUDA graph (GraphedTrainStep under data parallelism)."""
+        m = umask.reshape(-1).to(torch.float32)
+        w = m if weight is None else weight.to(m.device)[label.reshape(-1)] * m
+        den = w.sum().reshape(1)
+        dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
+        return den.reshape(())
+
 
 def init_from_env(backend: Optional[str] = None):
     """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns

@@ -134,15 +134,21 @@ class ClassifierTrainer:
         if train:
             optimizer.zero_grad()
         textf, visuf, acouf, umask, label = data.text, data.visual, data.acoustic, data.umask, data.label
+        den = None
         if self.grad_reducer is not None and train:
-            # global denominator sum(w[label]*umask) so that summed shard gradients equal the
-            # single-device gradient on the whole batch
-            self.loss_function.den_override = self.grad_reducer.global_nll_denominator(label, umask, self.loss_function.weight)
+            # global denominator sum(w[label]*umask) so that summed shard gradients equal the single-device gradient
+            # on the whole batch.  It stays on the device (one scalar all-reduce, no host read), so the
+            # step can be replayed from a CUDA graph: the kernel computes the local numerator (denominator 1) and the
+            # division by the global sum is a device-side scalar op.
+            den = self.grad_reducer.global_nll_denominator_tensor(label, umask, self.loss_function.weight)
+            self.loss_function.den_override = 1.0
         with torch.set_grad_enabled(train):
             log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf)
             lp_ = log_prob.transpose(0, 1).contiguous().view(-1, log_prob.size()[2])
             labels_ = label.view(-1)
             loss = self.loss_function(lp_, labels_, umask)
+            if den is not None:
+                loss = loss / den
         pred_ = torch.argmax(lp_, 1)
         if train:
             loss.backward()
@@ -172,8 +178,9 @@ class GraphedTrainStep:
         self._seen, self._graphs = set(), {}
         self.kernels_per_replay = {}   # shape key -> kernels of this library recorded in the graph
         self.last_key = None
-        if (gan is not None and gan.grad_reducer is not None) or (cls is not None and cls.grad_reducer is not None):
-            self.enabled = False   # the data-parallel collectives read host scalars per step; run those eagerly
+        # Data parallelism: the gradient all-reduces (NCCL) and the scalar all-reduce of the NLL denominator are device-
+        # side and are recorded with the rest of the step; if a backend cannot be captured, the step falls back to eager.
+        self.distributed = (gan is not None and gan.grad_reducer is not None) or (cls is not None and cls.grad_reducer is not None)
 
     def _body(self, batch: Batch):
         out = {}
@@ -203,9 +210,17 @@ class GraphedTrainStep:
                 from ._lib import lib
                 n0 = int(lib().cdll.ganffn_launch_count())
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                try:
+                    with torch.cuda.graph(graph):
+                        self.seeds.advance()
+                        out = self._body(static)
+                except Exception:
+                    if not self.distributed:
+                        raise
+                    self.enabled = False          # this process group cannot be captured: eager from now on
+                    torch.cuda.synchronize(dev)
                     self.seeds.advance()
-                    out = self._body(static)
+                    return self._body(batch)
                 self.kernels_per_replay[key] = int(lib().cdll.ganffn_launch_count()) - n0
                 self._graphs[key] = (graph, static, out)
             graph, static, out = self._graphs[key]
