@@ -11,6 +11,7 @@ namespace ganffn {
 
 unsigned long long g_launches = 0;
 int g_gemm_engine = GANFFN_GEMM_AUTO;
+int g_side_streams = 1;
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -106,6 +107,7 @@ const char* ganffn_last_error(void) { return g_err; }
 unsigned long long ganffn_launch_count(void) { return g_launches; }
 void ganffn_reset_launch_count(void) { g_launches = 0; }
 void ganffn_gemm_profile_enable(int on) { g_prof = on != 0; }
+int ganffn_set_side_streams(int on) { const int prev = g_side_streams; g_side_streams = on != 0; return prev; }
 int ganffn_gemm_profile_collect(int engine, double* total_ms, double* total_flops, int64_t* launches) {
   GANFFN_CHECK_ARG(total_ms && total_flops && launches, "gemm_profile_collect: null pointer");
   double ms = 0.0, fl = 0.0;

@@ -13,6 +13,7 @@ namespace ganffn {
 // ---- library state (defined in capi.cu) ------------------------------------------------
 extern unsigned long long g_launches;
 extern int g_gemm_engine;
+extern int g_side_streams;   // weight gradients on a side stream inside net_bwd (ganffn_set_side_streams)
 void set_error(const char* fmt, ...);
 
 #define GANFFN_CHECK_ARG(cond, ...)                \

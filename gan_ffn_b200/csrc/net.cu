@@ -130,7 +130,7 @@ SideCtx* side_ctx(cudaStream_t st) {
   static std::mutex mu;
   static std::map<cudaStream_t, SideCtx*> table;
   static const bool off = getenv("GANFFN_NO_WGRAD_STREAM") != nullptr;
-  if (off) return nullptr;
+  if (off || !g_side_streams) return nullptr;
   std::lock_guard<std::mutex> lk(mu);
   auto it = table.find(st);
   if (it != table.end()) return it->second;

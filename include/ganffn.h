@@ -63,6 +63,10 @@ void ganffn_reset_launch_count(void);
 /* Select the GEMM engine (GANFFN_GEMM_*); returns the previous value. */
 int ganffn_set_gemm_engine(int engine);
 
+/* Weight-gradient products of ganffn_net_bwd on a library-owned side stream (forked from / joined to `stream` by
+ * events; default on).  Returns the previous setting.  bench.py switches it off for its per-kernel roofline leg. */
+int ganffn_set_side_streams(int on);
+
 /* GEMM profiling for the roofline leg of bench.py: when enabled every GEMM (with its split-K
  * fold) is bracketed by CUDA events on the launching stream.  collect() synchronises, sums the
  * elapsed milliseconds and algorithmic FLOPs (2*M*N*K) of the GEMMs run by `engine`

@@ -13,7 +13,7 @@ from helpers import O
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = [1, 2]  # GANFFN_GEMM_SIMT, GANFFN_GEMM_TC (TC falls back to SIMT tiles for unsupported shapes)
+ENGINES = [0, 1, 2]  # GANFFN_GEMM_AUTO, _SIMT, _TC (TC falls back to SIMT tiles for unsupported shapes)
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +52,9 @@ def gemm_ws(L, M, N, K):
 LINEAR_SHAPES = [(300, 300, 100), (282, 2048, 100), (282, 100, 2048), (50, 1, 16), (37, 6, 100), (3008, 1536, 512),
                  (3008, 100, 2048), (3008, 2048, 512), (129, 512, 512), (1, 100, 100), (36, 64, 100), (36, 16, 64),
                  # K <= 128 and N >= 256: the A-stationary tcgen05 kernel (ragged M, N and K tails, several tiles per CTA)
-                 (3008, 2048, 100), (3008, 512, 100), (200, 1000, 64), (130, 260, 128), (6016, 2048, 100), (97, 4096, 36)]
+                 (3008, 2048, 100), (3008, 512, 100), (200, 1000, 64), (130, 260, 128), (6016, 2048, 100), (97, 4096, 36),
+                 # narrow outputs (out-proj and the dX products of the d=100 networks)
+                 (3008, 100, 100), (3008, 100, 300), (300, 100, 100), (6016, 128, 320), (257, 36, 64)]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -115,7 +117,8 @@ def test_dropout_mask_statistics_and_determinism(L):
 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("M,N,K", [(282, 2048, 100), (282, 100, 2048), (3008, 512, 2048), (3008, 1536, 512), (50, 1, 16),
-                                   (36, 16, 64), (3008, 100, 2048), (200, 64, 1000), (130, 128, 260)])
+                                   (36, 16, 64), (3008, 100, 2048), (200, 64, 1000), (130, 128, 260), (3008, 100, 100), (3008, 300, 100),
+                                   (300, 128, 36)])
 def test_linear_dgrad_and_wgrad(L, engine, M, N, K):
     L.cdll.ganffn_set_gemm_engine(engine)
     g = torch.Generator().manual_seed(M + N + K)
