@@ -230,16 +230,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float inv_sqrt_bc2, float b1, float b2, float eps, float wd,
                                                    float gscale, const int* __restrict__ step_dev) {
   if (step_dev != nullptr) {
-    const double step = (double)__ldg(step_dev);
-    lr_bc1 = (float)((double)lr_bc1 / (1.0 - pow((double)b1, step)));
-    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, step)));
+    // the fp64 pow / sqrt of the bias corrections once per block, not once per thread
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+      const double step = (double)__ldg(step_dev);
+      s_bc[0] = (float)((double)lr_bc1 / (1.0 - pow((double)b1, step)));
+      s_bc[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, step)));
+    }
+    __syncthreads();
+    lr_bc1 = s_bc[0];
+    inv_sqrt_bc2 = s_bc[1];
   }
   const int64_t nvec = n >> 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto update = [&](float4& pp, const float4& gg, float4& mm, float4& vv) {
     float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -248,6 +252,25 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
       pa[j] -= lr_bc1 * ma[j] / (sqrtf(va[j]) * inv_sqrt_bc2 + eps);
     }
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {   // two float4 per array in flight per thread (8 x 16 B requests)
+    const int64_t i2 = i + stride;
+    float4 p0 = reinterpret_cast<float4*>(p)[i], p1 = reinterpret_cast<float4*>(p)[i2];
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + i), g1 = __ldg(reinterpret_cast<const float4*>(g) + i2);
+    float4 m0 = reinterpret_cast<float4*>(m)[i], m1 = reinterpret_cast<float4*>(m)[i2];
+    float4 v0 = reinterpret_cast<float4*>(v)[i], v1 = reinterpret_cast<float4*>(v)[i2];
+    update(p0, g0, m0, v0);
+    update(p1, g1, m1, v1);
+    reinterpret_cast<float4*>(p)[i] = p0; reinterpret_cast<float4*>(m)[i] = m0; reinterpret_cast<float4*>(v)[i] = v0;
+    reinterpret_cast<float4*>(p)[i2] = p1; reinterpret_cast<float4*>(m)[i2] = m1; reinterpret_cast<float4*>(v)[i2] = v1;
+  }
+  for (; i < nvec; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    update(pp, gg, mm, vv);
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
