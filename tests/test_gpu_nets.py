@@ -286,6 +286,56 @@ def test_full_size_network_matches_oracle(nets, engine, name, B):
     m.zero_grad(set_to_none=True)
 
 
+@pytest.mark.parametrize("S,B", [(1, 1), (2, 3), (31, 2), (33, 5), (64, 1), (96, 2), (97, 2), (110, 3)])
+def test_edge_sequence_lengths_match_oracle(nets, S, B):
+    """Dialogue lengths around every boundary of the kernels: one turn, fewer turns than a warp, 32/33 (one / two row
+    warps), 96/97 (three / four row warps, 24 / 28 keys per warp group), and the PositionalEncoding maximum of 110;
+    ragged batches (real lengths below the pad length).  Outputs rtol 1e-4; gradients 1e-4 of the tensor scale."""
+    import gan_ffn_b200 as GB
+    ns, _ = nets
+    lengths = [S] + [max(1, S - 1 - 3 * i) for i in range(B - 1)]
+    batch = H.synthetic.make_batch(n_dialogues=B, lengths=lengths, seed=S * 7 + B)
+    for name in ("text_gen", "acoustic_disc"):
+        m = ns[name]
+        m.eval()
+        x_cpu = H.net_inputs(batch)[name]
+        m.zero_grad(set_to_none=True)
+        x = x_cpu.cuda().requires_grad_(True)
+        y = m(x)
+        cot = torch.rand(y.shape, generator=torch.Generator().manual_seed(3))
+        (y * cot.cuda()).sum().backward()
+        def oracle(dtype):
+            P = O.params_of(m, dtype=dtype, requires_grad=True)
+            xr = x_cpu.detach().clone().to(dtype).requires_grad_(True)
+            yr = H.oracle_forward(name, xr, P)
+            (yr * cot.to(dtype)).sum().backward()
+            return yr.detach().double(), xr.grad.double(), {k: v.grad.double() for k, v in P.items() if v.grad is not None}
+
+        y64, dx64, g64 = oracle(torch.float64)
+        _, dx32, g32 = oracle(torch.float32)
+        H.assert_close(y.detach().cpu(), y64, f"{name} S={S} B={B} output", atol_frac=1e-5)
+
+        def check(ours, e64, e32, what):
+            """Gradients: 1e-4 of the tensor scale, unless fp32 itself cannot decide a ReLU kink (then the fp32 oracle
+            shows the same kind of deviation from fp64): bounded maximum and rms, as in the full-size test."""
+            scale = float(e64.abs().max().clamp_min(1e-30))
+            err = (ours.detach().double().cpu() - e64).abs()
+            mx, mx32 = float(err.max()) / scale, float((e32 - e64).abs().max()) / scale
+            den = float(e64.pow(2).mean().sqrt().clamp_min(1e-30))
+            rms, rms32 = float(err.pow(2).mean().sqrt()) / den, float((e32 - e64).pow(2).mean().sqrt()) / den
+            # (one flipped kink moves the gradient rows of its whole dialogue by O(1e-3) of the scale, and with 1..5
+            # dialogues per case that is a large share of all entries: the rms bound is wider than at full size.  About
+            # 2.7 M pre-activations x a 1e-6-relative 3xTF32 band -> a few flips per case are expected.)
+            assert mx <= max(1e-4, 4 * mx32) or (mx <= 2e-2 and rms <= max(3e-3, 8 * rms32)), \
+                f"{what}: max {mx:.2e} (fp32 oracle {mx32:.2e}), rms {rms:.2e} (fp32 oracle {rms32:.2e}) of scale"
+
+        check(x.grad, dx64, dx32, f"{name} S={S} B={B} dx")
+        for n, p in m.named_parameters():
+            if p.grad is not None:
+                check(p.grad, g64[n], g32[n], f"{name} S={S} B={B} grad {n}")
+        m.zero_grad(set_to_none=True)
+
+
 def test_error_conventions(nets):
     ns, _ = nets
     g = ns["text_gen"]
