@@ -110,6 +110,7 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 
 _scratch: Dict[Tuple[str, int], torch.Tensor] = {}
+_scratch_retired: List[torch.Tensor] = []
 
 
 def _scratch_tag(device: torch.device) -> str:
@@ -126,6 +127,8 @@ def scratch(device: torch.device, floats: int, tag: str = "main") -> torch.Tenso
     key = (tag, device.index if device.index is not None else torch.cuda.current_device())
     buf = _scratch.get(key)
     if buf is None or buf.numel() < floats:
+        if buf is not None:
+            _scratch_retired.append(buf)   # a recorded CUDA graph may still hold this address: never free a workspace
         buf = torch.empty(max(int(floats), 1), dtype=torch.float32, device=device)
         _scratch[key] = buf
     return buf

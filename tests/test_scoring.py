@@ -58,3 +58,21 @@ def test_sharded_scoring_equals_unsharded_scoring():
     i_short, i_long = plan[0][0], plan[-1][-1]
     mixed = scoring.score_batch(ffn, corpus.batch([i_short, i_long]).to("cuda"))["log_prob"][:lengths[i_short], 0]
     assert not torch.allclose(mixed, ref[i_short][:lengths[i_short]], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_graphed_scorer_equals_eager_scoring():
+    from gan_ffn_b200 import train
+    nets, ffn = train.build_networks(n_classes=6, device="cuda")
+    lengths = [9, 9, 7, 9, 12, 12, 10, 12]
+    corpus = scoring.SyntheticDialogues(lengths)
+    scorer = scoring.GraphedScorer(ffn)
+    # two shapes; the small one is recorded before the large one is first seen (the workspace grows in between: a
+    # recorded graph must keep working), then both are revisited
+    batches = [[0, 1, 2, 3], [3, 2, 1, 0], [2, 3, 0, 1], [4, 5, 6, 7], [7, 6, 5, 4], [0, 1, 2, 3], [4, 5, 6, 7]]
+    for idx in batches:
+        b = corpus.batch(idx).to("cuda")
+        ref = scoring.score_batch(ffn, b)["log_prob"].clone()
+        got = scorer(b)["log_prob"]
+        assert torch.equal(got, ref), f"graph replay differs from eager scoring for batch {idx}"
+    assert len(scorer._graphs) == 2

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch-size", type=int, default=32)
     ap.add_argument("--meld", action="store_true", help="MELD-shaped: 7 classes, dialogues of 1..33 turns")
     ap.add_argument("--unsorted", action="store_true", help="keep loader order instead of grouping by length")
+    ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying one CUDA graph per batch shape")
     args = ap.parse_args()
     rank, local_rank, world = parallel.init_from_env()
     torch.cuda.set_device(local_rank)
@@ -58,9 +59,11 @@ def main():
 
     copy_stream = torch.cuda.Stream()
     L = lib()
-    # warm-up: every distinct shape once (workspace growth, lazy module state)
+    scorer = (lambda b: scoring.score_batch(ffn, b)) if args.eager else scoring.GraphedScorer(ffn)
+    # warm-up: every distinct shape (workspace growth, lazy module state; graph mode: eager call, then the recording)
     for key in keys:
-        scoring.score_batch(ffn, pool[key].to(dev))
+        for _ in range(1 if args.eager else 3):
+            scorer(pool[key].to(dev))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -82,7 +85,7 @@ def main():
             with torch.cuda.stream(copy_stream):
                 hb, s2, r2 = host_batch(mine[k + 1])
                 nxt = (hb.to(dev, non_blocking=True), s2, r2, hb.h2d_bytes())
-        out = scoring.score_batch(ffn, cur)
+        out = scorer(cur)
         p = out["pred"].to("cpu", non_blocking=True)
         d2h += p.numel() * p.element_size()
         preds.append(p)
@@ -112,6 +115,7 @@ def main():
                            "batching": "loader order" if args.unsorted else "sorted by length (ascending), whole batches dealt round-robin to ranks",
                            "parallelism": f"dp{world} by dialogue, no collective on the data path",
                            "host_data": f"{len(pool)} pinned host batches per rank (one per distinct pad length x batch size); every planned batch is copied from the host",
+                           "launch": "eager kernel launches" if args.eager else "one CUDA graph per batch shape, replayed",
                            "timing": "CUDA events around the whole sweep incl. host->device and device->host copies, max over ranks"},
                 "h2d_bytes": float(tsum[4]), "d2h_bytes": float(tsum[5]), "gpu_launches": int(L.cdll.ganffn_launch_count())}
         print(json.dumps(line), flush=True)
