@@ -947,20 +947,33 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __re
 struct TcPlan { int splits; int kps; };
 
 // Split-K for an accumulating (red.global.add) product: no fold kernel, so the only costs are the per-CTA
-// prologue / atomic epilogue and the waves.
+// prologue / atomic epilogue and the waves.  These are the weight-gradient products: they run on the side stream
+// of net_bwd, off the critical path, and the train step is bound by aggregate SM time -- so the
+// plan is the one with the least SM time (CTAs x cycles per CTA) among those within 2x of the lowest latency, not
+// the lowest-latency one (which splits K as finely as the SM count allows and pays the fixed CTA cost 144 times).
 TcPlan tc_plan_atomic(int M, int N, int K) {
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int nkb = cdiv(K, BK);
-  TcPlan best{1, (int)round_up(K, BK)};
-  double best_cost = 1e300;
+  struct Cand { TcPlan pl; double latency, sm_time; };
+  Cand cands[64];
+  int n = 0;
+  double best_latency = 1e300;
   for (int sp = 1; sp <= nkb && sp <= 64; ++sp) {
     const int kps = (int)round_up(cdiv(K, sp), BK);
     if (kps > 1024) continue;
     const int splits = cdiv(K, kps);
-    const int waves = cdiv((int64_t)tiles * splits, 148);
-    const double cost = waves * (cdiv(kps, BK) * 800.0 + 6000.0) + splits * 150.0;
-    if (cost < best_cost) { best_cost = cost; best = TcPlan{splits, kps}; }
+    const int ctas = tiles * splits;
+    const int waves = cdiv((int64_t)ctas, 148);
+    const double per_cta = cdiv(kps, BK) * 800.0 + 6000.0;
+    const double latency = waves * per_cta + splits * 150.0;
+    cands[n++] = Cand{TcPlan{splits, kps}, latency, ctas * per_cta};
+    best_latency = std::min(best_latency, latency);
   }
+  TcPlan best{1, (int)round_up(K, BK)};
+  double best_sm = 1e300;
+  static const double cap = getenv("GANFFN_WGRAD_CAP") ? atof(getenv("GANFFN_WGRAD_CAP")) : 2.0;   // tuning switch
+  for (int i = 0; i < n; ++i)
+    if (cands[i].latency <= cap * best_latency && cands[i].sm_time < best_sm) { best_sm = cands[i].sm_time; best = cands[i].pl; }
   return best;
 }
 
