@@ -79,3 +79,58 @@ def test_dp_step_equals_single_gpu_step(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     ok = torch.load(out)
     assert all(ok.values()), ok
+
+
+def _trainer_worker(rank, world, port, out_path):
+    """ClassifierTrainer under data parallelism, replayed from a CUDA graph (NCCL all-reduces and the device-resident
+    NLL denominator recorded with the step) against the single-GPU eager trainer on the whole global batch."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from gan_ffn_b200 import parallel, synthetic, train
+    parallel.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    red = parallel.GradReducer()
+    w = torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev)
+    glob = synthetic.make_batch(n_dialogues=6, lengths=[40, 17, 33, 8, 25, 40], seed=9)
+
+    def run(batch, reducer, graphed):
+        nets, ffn = train.build_networks(device=dev)
+        ffn.eval()
+        ffn.train = lambda mode=True: ffn          # keep dropout off: the comparison must be deterministic
+        cls = train.ClassifierTrainer(ffn, w, grad_reducer=reducer)
+        stepper = train.GraphedTrainStep(None, cls, seed=5, enabled=graphed)
+        b = batch.to(dev)
+        losses = []
+        for _ in range(4):                          # graphed: eager, record, replay, replay
+            losses.append(stepper(b)["loss"].detach().clone())
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().reshape(-1) for p in ffn.parameters()])
+        return torch.stack(losses), flat, bool(stepper.kernels_per_replay)
+
+    l_dp, w_dp, captured = run(parallel.shard_batch(glob, world, rank), red, True)
+    dist.all_reduce(l_dp)                           # each rank holds local numerator / global denominator
+    l_one, w_one, _ = run(glob, None, False)
+    ok = {"captured_under_dp": captured,
+          "loss_step0": bool(torch.allclose(l_dp[0], l_one[0], rtol=1e-4, atol=0)),
+          "loss_later": bool(torch.allclose(l_dp, l_one, rtol=2e-3, atol=0)),
+          "weights": float((w_dp - w_one).abs().mean()) < 0.1 * 1e-4}
+    if rank == 0:
+        torch.save(ok, out_path)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)      # no communicator teardown under live recorded collectives (see bench.py)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_dp_trainer_graph_replay_equals_single_gpu_trainer(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ok.pt")
+    ctx = mp.spawn(_trainer_worker, args=(2, _free_port(), out), nprocs=2, join=False)
+    for p in ctx.processes:
+        p.join(timeout=300)
+        assert p.exitcode == 0, f"worker exit code {p.exitcode}"
+    ok = torch.load(out)
+    assert all(ok.values()), ok
