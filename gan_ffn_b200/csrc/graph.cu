@@ -283,11 +283,21 @@ __global__ void __launch_bounds__(256) graph_gather_dialogue_kernel(const float*
     const int t0 = (TYPED && lane < deg0) ? etype[beg + lane] : -1;
     if (TYPED) {
       float4* ov = reinterpret_cast<float4*>(out) + n * R * d4;
+      const float w_lane = lane < R ? __ldg(inv_cnt + n * R + lane) : 0.f;   // R <= 32: one coalesced load per row
+      const bool short_row = end - beg <= 32;
       for (int r = 0; r < R; ++r) {
+        unsigned m = __ballot_sync(0xffffffffu, t0 == r);
+        if (m == 0 && short_row) {           // empty relation: zeros, nothing to accumulate or scale
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d4) ov[(int64_t)r * d4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          continue;
+        }
         float4 acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned m = __ballot_sync(0xffffffffu, t0 == r);
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(256) graph_gather_dialogue_kernel(const float*
             }
           }
         }
-        const float w = inv_cnt[n * R + r];
+        const float w = R <= 32 ? __shfl_sync(0xffffffffu, w_lane, r) : inv_cnt[n * R + r];
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           const int c = lane + 32 * k;
@@ -319,12 +329,31 @@ __global__ void __launch_bounds__(256) graph_gather_dialogue_kernel(const float*
       float4 acc[NV];
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < deg0; ++s) {
-        const int j = __shfl_sync(0xffffffffu, c0, s);
+      // Sources of a row are ascending and unique, so last - first == deg - 1 means a contiguous run (every row of a
+      // window graph): the neighbour rows are then xs[first], xs[first + 1], ... -- no shuffle, no index arithmetic.
+      const int c_first = __shfl_sync(0xffffffffu, c0, 0);
+      const int c_last = __shfl_sync(0xffffffffu, c0, deg0 > 0 ? deg0 - 1 : 0);
+      if (deg0 > 0 && c_last - c_first == deg0 - 1) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           const int c = lane + 32 * k;
-          if (c < d4) add4(acc[k], xs[j * d4 + c], 1.f);
+          if (c < d4) {
+            const float4* row = xs + c_first * d4 + c;
+#pragma unroll 4
+            for (int s = 0; s < deg0; ++s) {
+              const float4 v = row[s * d4];
+              acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+            }
+          }
+        }
+      } else {
+        for (int s = 0; s < deg0; ++s) {
+          const int j = __shfl_sync(0xffffffffu, c0, s);
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d4) add4(acc[k], xs[j * d4 + c], 1.f);
+          }
         }
       }
       for (int64_t e = beg + 32; e < end; ++e) {
