@@ -370,18 +370,13 @@ def run_ours(args):
             line["graph"] = graph
         print(json.dumps(line), flush=True)
     if world > 1:
-        # The replayed graphs hold the recorded NCCL kernels: release them, drain the device, then leave without tearing
-        # the communicator down (ncclCommDestroy under live captured collectives can wait forever; the processes
-        # exit right after, which releases everything).
-        stepper._graphs.clear()
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
+        # orderly teardown: drop the recorded graphs (they hold the captured NCCL kernels) -> drain -> barrier ->
+        # destroy the group, under a watchdog (parallel.shutdown); only a teardown that does not return is cut short
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        if not parallel.shutdown([stepper]):
+            print(f"[rank {rank}] process-group teardown did not return in 30 s; exiting the process", file=sys.stderr, flush=True)
+            os._exit(0)
 
 
 def main():

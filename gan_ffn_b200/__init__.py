@@ -8,8 +8,8 @@ from .model import (AcousticDiscriminator, AcousticGenerator, BCELoss, GAN_FFN, 
                     PositionalEncoding,
                     TextDiscriminator, TextGenerator, VisualDiscriminator, VisualGenerator)
 from .optim import FusedAdam
-from .functional import manual_seed
+from .functional import manual_seed, set_deterministic
 
 __all__ = ["AcousticGenerator", "VisualGenerator", "TextGenerator", "AcousticDiscriminator", "VisualDiscriminator",
            "TextDiscriminator", "GAN_FFN", "GAN_FFN_DialogueRNN", "MaskedNLLLoss", "BCELoss", "PositionalEncoding", "FusedAdam",
-           "manual_seed"]
+           "manual_seed", "set_deterministic"]

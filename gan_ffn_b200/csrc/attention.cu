@@ -590,21 +590,13 @@ int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int 
                cudaStream_t st) {
   if constexpr (HD <= 16) {
     auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)2 * NG * s + (size_t)(NG - 1) * s * (HD | 1)) * sizeof(float); };
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(attention_fwd_small_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(GANFFN_MAX_SEQ));
-      attr_done = true;
-    }
+    GANFFN_SMEM_OPTIN(attention_fwd_small_kernel<HD>, bytes(GANFFN_MAX_SEQ));
     attention_fwd_small_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
     GANFFN_LAUNCHED("attention_fwd_small_kernel");
     return GANFFN_OK;
   } else {
   auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)s * (s | 1) + (size_t)NG * s) * sizeof(float); };
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(GANFFN_MAX_SEQ));
-    attr_done = true;
-  }
+  GANFFN_SMEM_OPTIN(attention_fwd_kernel<HD>, bytes(GANFFN_MAX_SEQ));
   attention_fwd_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
   GANFFN_LAUNCHED("attention_fwd_kernel");
   return GANFFN_OK;
@@ -616,23 +608,14 @@ int launch_bwd(const float* qkv, const float* o, const float* lse, const float* 
                int nhead, float p, Seed seed, int site, cudaStream_t st) {
   if constexpr (HD <= 16) {
     auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s * (s | 1) + (size_t)(NG - 1) * s * ((2 * HD) | 1)) * sizeof(float); };
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(attention_bwd_small_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(GANFFN_MAX_SEQ));
-      attr_done = true;
-    }
+    GANFFN_SMEM_OPTIN(attention_bwd_small_kernel<HD>, bytes(GANFFN_MAX_SEQ));
     attention_bwd_small_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
                                                                                (uint32_t)site);
     GANFFN_LAUNCHED("attention_bwd_small_kernel");
     return GANFFN_OK;
   } else {
   auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s * (s | 1) + s) * sizeof(float); };
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)bytes(GANFFN_MAX_SEQ));
-    attr_done = true;
-  }
+  GANFFN_SMEM_OPTIN(attention_bwd_kernel<HD>, bytes(GANFFN_MAX_SEQ));
   attention_bwd_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
                                                                        (uint32_t)site);
   GANFFN_LAUNCHED("attention_bwd_kernel");

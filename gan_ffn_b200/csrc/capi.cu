@@ -12,6 +12,7 @@ namespace ganffn {
 unsigned long long g_launches = 0;
 int g_gemm_engine = GANFFN_GEMM_AUTO;
 int g_side_streams = 1;
+int g_deterministic = 0;
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -80,6 +81,16 @@ int linear_wgrad(const float* dy, const float* x, float* dw, float* db, int M, i
     cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st);
     if (db) cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
   }
+  if (g_deterministic) {
+    // Fixed-order accumulation: dw = 1 * dw + dy^T x through the non-atomic path (split-K partials folded in slice
+    // order by the reduce kernel), bias gradient by the single-writer column sum.  One backward pass at a time
+    // may add to an arena in this mode (the host side runs the networks serially).
+    Epilogue ep;
+    ep.beta = 1.0f;
+    GANFFN_TRY(gemm(dy, N, true, x, K, false, dw, K, N, K, M, ep, gemm_scratch, gemm_scratch_n, st));
+    if (db) GANFFN_TRY(colsum(dy, M, N, db, 1, st));
+    return GANFFN_OK;
+  }
   Epilogue ep;
   ep.atomic_acc = 1;
   const bool tc = gemm_uses_tc(dy, N, true, x, K, false, K, N, K, M);
@@ -107,6 +118,7 @@ const char* ganffn_last_error(void) { return g_err; }
 unsigned long long ganffn_launch_count(void) { return g_launches; }
 void ganffn_reset_launch_count(void) { g_launches = 0; }
 void ganffn_gemm_profile_enable(int on) { g_prof = on != 0; }
+int ganffn_set_deterministic(int on) { const int prev = g_deterministic; g_deterministic = on != 0; return prev; }
 int ganffn_set_side_streams(int on) { const int prev = g_side_streams; g_side_streams = on != 0; return prev; }
 int ganffn_gemm_profile_collect(int engine, double* total_ms, double* total_flops, int64_t* launches) {
   GANFFN_CHECK_ARG(total_ms && total_flops && launches, "gemm_profile_collect: null pointer");

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <math.h>
 #include <algorithm>
+#include <atomic>
 
 #include "../../include/ganffn.h"
 
@@ -13,6 +14,7 @@ namespace ganffn {
 // ---- library state (defined in capi.cu) ------------------------------------------------
 extern unsigned long long g_launches;
 extern int g_gemm_engine;
+extern int g_deterministic;  // fixed-order gradient accumulation (ganffn_set_deterministic)
 extern int g_side_streams;   // weight gradients on a side stream inside net_bwd (ganffn_set_side_streams)
 void set_error(const char* fmt, ...);
 
@@ -39,6 +41,21 @@ void set_error(const char* fmt, ...);
   do {                               \
     int rc__ = (expr);               \
     if (rc__ != GANFFN_OK) return rc__; \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: opt in once per (kernel, device).  One
+// static bit mask per call site (= per kernel instantiation); the atomic makes the check safe between the main
+// thread and autograd's worker thread (setting the attribute twice is harmless).
+#define GANFFN_SMEM_OPTIN(kernel, bytes)                                                                  \
+  do {                                                                                                    \
+    static std::atomic<unsigned long long> done__{0ull};                                                  \
+    int dev__ = 0;                                                                                        \
+    cudaGetDevice(&dev__);                                                                                \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                                              \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
+      done__.fetch_or(bit__, std::memory_order_release);                                                  \
+    }                                                                                                     \
   } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

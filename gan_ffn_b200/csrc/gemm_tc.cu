@@ -1000,13 +1000,9 @@ TcPlan tc_plan(int M, int N, int K) {
 
 template <bool TA, bool TB>
 int launch_tc2(const TcParams& p, int epi, dim3 grid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, EPI_DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    attr_done = true;
-  }
+  GANFFN_SMEM_OPTIN((gemm_tc_kernel<TA, TB, EPI_PLAIN>), SMEM);
+  GANFFN_SMEM_OPTIN((gemm_tc_kernel<TA, TB, EPI_DROP>), SMEM);
+  GANFFN_SMEM_OPTIN((gemm_tc_kernel<TA, TB, EPI_FULL>), SMEM);
   if (epi == EPI_PLAIN) gemm_tc_kernel<TA, TB, EPI_PLAIN><<<grid, NTHREADS, SMEM, st>>>(p);
   else if (epi == EPI_DROP) gemm_tc_kernel<TA, TB, EPI_DROP><<<grid, NTHREADS, SMEM, st>>>(p);
   else gemm_tc_kernel<TA, TB, EPI_FULL><<<grid, NTHREADS, SMEM, st>>>(p);
@@ -1023,13 +1019,9 @@ int launch_tc(const TcParams& p, bool TA, bool TB, int epi, dim3 grid, cudaStrea
 
 template <bool TB>
 int launch_astat2(const TcParams& p, int epi, dim3 grid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_astat_kernel<TB, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMEM);
-    cudaFuncSetAttribute(gemm_tc_astat_kernel<TB, EPI_DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMEM);
-    cudaFuncSetAttribute(gemm_tc_astat_kernel<TB, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMEM);
-    attr_done = true;
-  }
+  GANFFN_SMEM_OPTIN((gemm_tc_astat_kernel<TB, EPI_PLAIN>), ASMEM);
+  GANFFN_SMEM_OPTIN((gemm_tc_astat_kernel<TB, EPI_DROP>), ASMEM);
+  GANFFN_SMEM_OPTIN((gemm_tc_astat_kernel<TB, EPI_FULL>), ASMEM);
   if (epi == EPI_PLAIN) gemm_tc_astat_kernel<TB, EPI_PLAIN><<<grid, A_NTHREADS, ASMEM, st>>>(p);
   else if (epi == EPI_DROP) gemm_tc_astat_kernel<TB, EPI_DROP><<<grid, A_NTHREADS, ASMEM, st>>>(p);
   else gemm_tc_astat_kernel<TB, EPI_FULL><<<grid, A_NTHREADS, ASMEM, st>>>(p);

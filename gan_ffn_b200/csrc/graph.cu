@@ -380,12 +380,17 @@ template <bool TYPED, int NV>
 int launch_gather_dialogue(const float* x, const int64_t* node_off, int B, int max_len, const int64_t* rowptr, const int* col,
                            const int* etype, const float* inv_cnt, float* out, int R, int d, cudaStream_t st) {
   const size_t smem = (size_t)max_len * d * sizeof(float);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaFuncSetAttribute(graph_gather_dialogue_kernel<TYPED, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GATHER_SMEM_MAX);
-    // several 44 KB dialogues per SM: ask for the largest shared-memory carve-out
-    cudaFuncSetAttribute(graph_gather_dialogue_kernel<TYPED, NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr = GATHER_SMEM_MAX;
+  {
+    // per-device attributes (several 44 KB dialogues per SM: also ask for the largest shared-memory carve-out)
+    static std::atomic<unsigned long long> done{0ull};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+      cudaFuncSetAttribute(graph_gather_dialogue_kernel<TYPED, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GATHER_SMEM_MAX);
+      cudaFuncSetAttribute(graph_gather_dialogue_kernel<TYPED, NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      done.fetch_or(bit, std::memory_order_release);
+    }
   }
   graph_gather_dialogue_kernel<TYPED, NV><<<B, 256, smem, st>>>(x, node_off, rowptr, col, etype, inv_cnt, out, R, d / 4);
   GANFFN_LAUNCHED("graph_gather_dialogue_kernel");

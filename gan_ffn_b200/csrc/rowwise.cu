@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // ---- LayerNorm backward -----------------------------------------------------------------------------
+constexpr int LN_BWD_MAX_BLOCKS = 148 * 2;
+__device__ float g_ln_partial[LN_BWD_MAX_BLOCKS * 3 * 512];   // deterministic mode only (see the kernel's tail)
+__device__ unsigned g_ln_counter = 0u;
 // dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Each block folds its warps in shared memory
 // and adds its dgamma / dbeta / sublayer-bias-gradient partials to the (pre-zeroed or accumulating) outputs
 // with red.global.add: no partial buffer and no second kernel (r1 launch list: 836 fold launches per step).
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma, float* __restrict__ dz,
                                                             float* __restrict__ dz_drop, float* dgamma, float* dbeta,
                                                             float* dbias_sub, int T, int d, float p_drop, const Seed seed_ref,
-                                                            uint32_t site) {
+                                                            uint32_t site, int det) {
   extern __shared__ __align__(16) float sm[];  // [warps][3][d]: dgamma, dbeta, colsum(dz after dropout)
   const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = d >> 2;
@@ -187,14 +190,41 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
   }
   __syncthreads();
+  if (!det) {
+    for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
+      const int seg = c / d;
+      float* out = seg == 0 ? dgamma : seg == 1 ? dbeta : dbias_sub;
+      if (out == nullptr) continue;
+      float s = 0.f;
+      for (int ww = 0; ww < warps; ++ww) s += sm[(size_t)ww * 3 * d + c];
+      atomicAdd(out + (c - seg * d), s);
+    }
+    return;
+  }
+  // Deterministic mode (ganffn_set_deterministic): block partials go to a static device buffer, the block that
+  // finishes last folds them in block order and does the one read-modify-write per output element.  The buffer is
+  // per device, so at most one LayerNorm backward may be in flight (deterministic mode runs networks serially).
+  for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
+    float s = 0.f;
+    for (int ww = 0; ww < warps; ++ww) s += sm[(size_t)ww * 3 * d + c];
+    g_ln_partial[(size_t)blockIdx.x * 3 * d + c] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned ticket;
+  if (threadIdx.x == 0) ticket = atomicAdd(&g_ln_counter, 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
   for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
     const int seg = c / d;
     float* out = seg == 0 ? dgamma : seg == 1 ? dbeta : dbias_sub;
     if (out == nullptr) continue;
     float s = 0.f;
-    for (int ww = 0; ww < warps; ++ww) s += sm[(size_t)ww * 3 * d + c];
-    atomicAdd(out + (c - seg * d), s);
+    for (unsigned bb = 0; bb < gridDim.x; ++bb) s += __ldcg(&g_ln_partial[(size_t)bb * 3 * d + c]);
+    out[c - seg * d] += s;
   }
+  if (threadIdx.x == 0) g_ln_counter = 0u;
 }
 
 // ---- positional encoding ------------------------------------------------------------------------------
@@ -314,10 +344,10 @@ int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz
   const size_t smem = (size_t)8 * 3 * d * sizeof(float);
   if (d <= 128) {
     layernorm_bwd_kernel<1, 4><<<min(cdiv(T, 8 * 4), 148 * 2), 256, smem, st>>>(dy, z, gamma, dz, dz_drop, dgamma, dbeta, dbias_sub,
-                                                                             T, d, p, seed, (uint32_t)site);
+                                                                             T, d, p, seed, (uint32_t)site, g_deterministic);
   } else {
     layernorm_bwd_kernel<LN_MAXV, 1><<<ln_bwd_blocks(T), 256, smem, st>>>(dy, z, gamma, dz, dz_drop, dgamma, dbeta, dbias_sub, T, d,
-                                                                        p, seed, (uint32_t)site);
+                                                                        p, seed, (uint32_t)site, g_deterministic);
   }
   GANFFN_LAUNCHED("layernorm_bwd_kernel");
   return GANFFN_OK;
@@ -353,7 +383,9 @@ static int colsum_rowblocks(int M, int N) {
 // out[N] (+)= column sums of a[M,N]
 int colsum(const float* a, int M, int N, float* out, int accumulate, cudaStream_t st) {
   if (!accumulate) cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
-  const int yb = colsum_rowblocks(M, N);
+  // deterministic mode: one block per 32-column strip sums all rows in a fixed order (the kernel's red.global.add
+  // is then the only writer of its element)
+  const int yb = g_deterministic ? 1 : colsum_rowblocks(M, N);
   const int rpb = cdiv(M, yb);
   dim3 grid(cdiv(N, 32), yb);
   colsum_kernel<<<grid, 256, 0, st>>>(a, M, N, rpb, out);

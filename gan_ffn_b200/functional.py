@@ -100,6 +100,17 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _call(t: torch.Tensor, name: str, *args) -> None:
+    """C-ABI call with ``t``'s device current: the kernels launch on (and opt their shared memory in for) the
+    current device, which need not be the tensor's in a process that drives several GPUs."""
+    idx = t.device.index
+    if idx is not None and idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):
+            lib().call(name, *args)
+    else:
+        lib().call(name, *args)
+
+
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -202,7 +213,7 @@ class overlap_networks:
 
     def __enter__(self):
         self.prev = _lanes.active
-        if self.enabled:
+        if self.enabled and not _deterministic["on"]:
             _lanes.n = self.lanes
             _lanes.active = True
         return self
@@ -215,6 +226,20 @@ class overlap_networks:
 
 def join_lanes() -> None:
     _lanes.join()
+
+
+_deterministic = {"on": False}
+
+
+def set_deterministic(on: bool = True) -> bool:
+    """Bit-reproducible training steps (the reference pins determinism, train_IEMOCAP.py:46-53): the kernels
+    accumulate gradients in a fixed order (``ganffn_set_deterministic``) and the networks of a loop body run serially
+    instead of on concurrent lanes (two backward passes must not add to one arena at the same time).  Costs
+    throughput; off by default.  Returns the previous setting."""
+    prev = _deterministic["on"]
+    _deterministic["on"] = bool(on)
+    lib().cdll.ganffn_set_deterministic(int(bool(on)))
+    return prev
 
 
 def _al(n: int, a: int = 32) -> int:
@@ -305,7 +330,7 @@ class _NetFunction(torch.autograd.Function):
         stash = torch.empty(stash_n, dtype=torch.float32, device=x.device)
         ws = scratch(x.device, scratch_n, _scratch_tag(x.device))
         out = torch.empty((S, B, spec.h2 if spec.kind == 0 else 1), dtype=torch.float32, device=x.device)
-        L.call("ganffn_net_fwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(pe), ptr(x), ptr(out),
+        _call(x, "ganffn_net_fwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(pe), ptr(x), ptr(out),
                ptr(stash), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff, spec.nlayers, spec.h1, spec.h2,
                int(train), float(p_head), seed, seed_ptr, _stream(x))
         ctx.arena, ctx.spec, ctx.train, ctx.p_head, ctx.seed, ctx.seed_ptr = arena, spec, train, p_head, seed, seed_ptr
@@ -338,7 +363,7 @@ class _NetFunction(torch.autograd.Function):
             arena.install_grads()
         elif arena.zero_event is not None and arena.zero_stream != cur.cuda_stream:
             cur.wait_event(arena.zero_event)   # another lane zeroed the arena for this backward pass
-        L.call("ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
+        _call(x, "ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
                ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
                spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, ctx.seed_ptr, 1, _stream(x))
         ctx.stash = None
@@ -391,7 +416,7 @@ class _FuseClsFunction(torch.autograd.Function):
         a, v, t, w, b = a.contiguous(), v.contiguous(), t.contiguous(), w.contiguous(), b.contiguous()
         fusion = torch.empty((S, B, dh), dtype=torch.float32, device=a.device)
         logp = torch.empty((S, B, C), dtype=torch.float32, device=a.device)
-        L.call("ganffn_fuse_cls_fwd", ptr(a), ptr(v), ptr(t), ptr(w), ptr(b), ptr(fusion), ptr(logp), T, dh, C,
+        _call(a, "ganffn_fuse_cls_fwd", ptr(a), ptr(v), ptr(t), ptr(w), ptr(b), ptr(fusion), ptr(logp), T, dh, C,
                _stream(a))
         ctx.save_for_backward(fusion, logp, w)
         return logp
@@ -408,7 +433,7 @@ class _FuseClsFunction(torch.autograd.Function):
         dw = torch.empty_like(w)
         db = torch.empty(C, dtype=torch.float32, device=w.device)
         ws = scratch(w.device, L.query("ganffn_fuse_cls_scratch_floats", T, dh, C), "cls")
-        L.call("ganffn_fuse_cls_bwd", ptr(d_logp), ptr(logp), ptr(fusion), ptr(w), ptr(d_fusion), ptr(dw), ptr(db), T,
+        _call(w, "ganffn_fuse_cls_bwd", ptr(d_logp), ptr(logp), ptr(fusion), ptr(w), ptr(d_fusion), ptr(dw), ptr(db), T,
                dh, C, 0, ptr(ws), _stream(w))
         return d_fusion, d_fusion, d_fusion, dw, db
 
@@ -430,7 +455,7 @@ class _MaskedNLLFunction(torch.autograd.Function):
         n, C = pred.shape
         pred = pred.contiguous()
         out = torch.empty(2, dtype=torch.float32, device=pred.device)
-        L.call("ganffn_masked_nll_fwd", ptr(pred), ptr(target), ptr(mask), ptr(weight), ptr(out), n, C,
+        _call(pred, "ganffn_masked_nll_fwd", ptr(pred), ptr(target), ptr(mask), ptr(weight), ptr(out), n, C,
                float(den_override), _stream(pred))
         ctx.save_for_backward(target, mask)
         ctx.out, ctx.weight, ctx.shape = out, weight, (n, C)
@@ -444,7 +469,7 @@ class _MaskedNLLFunction(torch.autograd.Function):
         n, C = ctx.shape
         d_loss = d_loss.contiguous()
         d_pred = torch.empty((n, C), dtype=torch.float32, device=out.device)
-        L.call("ganffn_masked_nll_bwd", ptr(d_loss), ptr(out), ptr(target), ptr(mask), ptr(ctx.weight), ptr(d_pred), n,
+        _call(out, "ganffn_masked_nll_bwd", ptr(d_loss), ptr(out), ptr(target), ptr(mask), ptr(ctx.weight), ptr(d_pred), n,
                C, _stream(out))
         return d_pred, None, None, None, None
 
@@ -469,7 +494,7 @@ class _BCEFunction(torch.autograd.Function):
         L = lib()
         prob, target = prob.contiguous(), target.contiguous()
         out = torch.empty(1, dtype=torch.float32, device=prob.device)
-        L.call("ganffn_bce_fwd", ptr(prob), ptr(target), ptr(out), prob.numel(), float(scale), _stream(prob))
+        _call(prob, "ganffn_bce_fwd", ptr(prob), ptr(target), ptr(out), prob.numel(), float(scale), _stream(prob))
         ctx.save_for_backward(prob, target)
         ctx.scale = scale
         return out.view(())
@@ -480,7 +505,7 @@ class _BCEFunction(torch.autograd.Function):
         prob, target = ctx.saved_tensors
         d_loss = d_loss.contiguous()
         d_prob = torch.empty_like(prob)
-        L.call("ganffn_bce_bwd", ptr(d_loss), ptr(prob), ptr(target), ptr(d_prob), prob.numel(), float(ctx.scale),
+        _call(prob, "ganffn_bce_bwd", ptr(d_loss), ptr(prob), ptr(target), ptr(d_prob), prob.numel(), float(ctx.scale),
                _stream(prob))
         return d_prob, None, None
 
@@ -500,6 +525,6 @@ def bce(prob, target, scale: float = 1.0):
 def dropout_mask(rows: int, cols: int, p: float, seed: int, site: int, row_stride: Optional[int] = None,
                  device="cuda") -> torch.Tensor:
     out = torch.empty((rows, cols), dtype=torch.float32, device=device)
-    lib().call("ganffn_dropout_mask", ptr(out), rows, cols, cols if row_stride is None else row_stride, float(p),
+    _call(out, "ganffn_dropout_mask", ptr(out), rows, cols, cols if row_stride is None else row_stride, float(p),
                seed, site, _stream(out))
     return out

@@ -281,11 +281,14 @@ class MaskedNLLLoss(nn.Module):
 
 class BCELoss(nn.Module):
     """``torch.nn.BCELoss()`` as used at reference train_IEMOCAP.py:300 (mean reduction).
-    ``scale`` multiplies the mean (1/world_size under dialogue sharding)."""
+    ``scale`` (host float) and ``scale_tensor`` (device scalar, CUDA-graph safe) multiply the mean: under dialogue
+    sharding a rank contributes local_mean * B_local / B_global."""
 
     def __init__(self):
         super().__init__()
         self.scale = 1.0
+        self.scale_tensor = None
 
     def forward(self, input, target):
-        return GF.bce(input, target, self.scale)
+        loss = GF.bce(input, target, self.scale)
+        return loss if self.scale_tensor is None else loss * self.scale_tensor

@@ -98,10 +98,10 @@ class FusedAdam:
             self.grad_reducer.reduce([ar.grad for ar in live] + [p.grad for p in loose])
         for ar in live:
             st = self._state_for(ar, ar.flat)
-            L.call("ganffn_adam_step_dev", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel,
+            GF._call(ar.flat, "ganffn_adam_step_dev", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel,
                    ptr(st["step_t"]), lr, b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(ar.flat))
         for p in loose:
             st = self._state_for(p, p)
             g = p.grad.contiguous()
-            L.call("ganffn_adam_step_dev", ptr(p), ptr(g), ptr(st["m"]), ptr(st["v"]), p.numel(), ptr(st["step_t"]), lr,
+            GF._call(p, "ganffn_adam_step_dev", ptr(p), ptr(g), ptr(st["m"]), ptr(st["v"]), p.numel(), ptr(st["step_t"]), lr,
                    b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(p))

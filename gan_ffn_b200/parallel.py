@@ -61,6 +61,20 @@ class GradReducer:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return float(t.item())
 
+    def local_fraction_tensor(self, local_count: int, device) -> torch.Tensor:
+        """local_count / (sum of local_count over the group) as a device scalar.  Every rank calls this for every
+        batch (so the collective sequence is the same on all ranks whatever the shard sizes are); the value never
+        touches the host, hence the call can be recorded into a CUDA graph."""
+        mine = torch.full((1,), float(local_count), dtype=torch.float32, device=device)
+        tot = mine.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+        return (mine / tot).reshape(())
+
+    def sum_tensor(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum of a device tensor over the group (loss logging under data parallelism)."""
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def global_nll_denominator(self, label: torch.Tensor, umask: torch.Tensor, weight: Optional[torch.Tensor]) -> float:
         """sum over the *global* batch of w[label]*umask (MaskedNLLLoss denominator, model.py:78-80)."""
         m = umask.reshape(-1).to(torch.float32)
@@ -95,3 +109,31 @@ def init_from_env(backend: Optional[str] = None):
         else:
             dist.init_process_group(backend)
     return rank, local_rank, world
+
+
+def shutdown(steppers=(), timeout_s: float = 30.0) -> bool:
+    """Orderly teardown of a data-parallel process: release recorded CUDA graphs (they reference the communicator's
+    kernels), drain the device, barrier, then destroy the process group.  ``destroy_process_group`` runs under a
+    watchdog: if the backend does not return within ``timeout_s`` the function reports False and the caller decides
+    (bench.py then exits the process, which releases everything).  Returns True on a clean teardown."""
+    import threading
+    for st in steppers:
+        st.release()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not dist.is_initialized():
+        return True
+    dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.destroy_process_group()
+        finally:
+            done.set()
+
+    th = threading.Thread(target=_destroy, daemon=True)
+    th.start()
+    return done.wait(timeout_s)

@@ -73,7 +73,6 @@ class GANTrainer:
         self.opt_text_D = mk(text_disc, lr / 2)
         self.adversarial_loss = M.BCELoss()
         self.grad_reducer, self.world_size = grad_reducer, world_size
-        self._bce_scale = {}
         # independent networks of a sub-step on concurrent streams (functional._Lanes); the loop bodies are unchanged
         self.overlap = overlap
 
@@ -93,10 +92,11 @@ class GANTrainer:
         adv = self.adversarial_loss
         # BCELoss is a mean over the *global* S*B slots: each rank contributes local_mean * (B_local / B_global)
         # (= 1/world_size for equal shards), so the summed shard gradients equal the single-device gradient.
+        # The global batch size is all-reduced on the device for EVERY batch by EVERY rank (never cached by the local
+        # size: with uneven last batches ranks would disagree on whether a collective is due and pair a scalar
+        # all-reduce with a gradient all-reduce); the scale stays a device scalar, so the step is still capturable.
         if self.grad_reducer is not None:
-            if batch_size not in self._bce_scale:
-                self._bce_scale[batch_size] = batch_size / self.grad_reducer.global_sum(batch_size, real_text.device)
-            adv.scale = self._bce_scale[batch_size]
+            adv.scale_tensor = self.grad_reducer.local_fraction_tensor(batch_size, real_text.device)
         loss = {}
         loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["acoustic_gen"], real_acoustic, self.opt_visual_D, adv, valid, fake)
         loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["visual_disc"], self.opt_acoustic_G, adv, valid, fake)
@@ -135,25 +135,35 @@ class ClassifierTrainer:
             optimizer.zero_grad()
         textf, visuf, acouf, umask, label = data.text, data.visual, data.acoustic, data.umask, data.label
         den = None
+        prev_override = self.loss_function.den_override
         if self.grad_reducer is not None and train:
             # global denominator sum(w[label]*umask) so that summed shard gradients equal the single-device gradient
             # on the whole batch.  It stays on the device (one scalar all-reduce, no host read), so the
             # step can be replayed from a CUDA graph: the kernel computes the local numerator (denominator 1) and the
             # division by the global sum is a device-side scalar op.
             den = self.grad_reducer.global_nll_denominator_tensor(label, umask, self.loss_function.weight)
-            self.loss_function.den_override = 1.0
-        with torch.set_grad_enabled(train):
-            log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf)
-            lp_ = log_prob.transpose(0, 1).contiguous().view(-1, log_prob.size()[2])
-            labels_ = label.view(-1)
-            loss = self.loss_function(lp_, labels_, umask)
-            if den is not None:
-                loss = loss / den
+        try:
+            # the override is scoped to this call: a later eval step must get the plain local mean again
+            self.loss_function.den_override = 1.0 if den is not None else 0.0
+            with torch.set_grad_enabled(train):
+                log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf)
+                lp_ = log_prob.transpose(0, 1).contiguous().view(-1, log_prob.size()[2])
+                labels_ = label.view(-1)
+                loss = self.loss_function(lp_, labels_, umask)
+                if den is not None:
+                    loss = loss / den
+        finally:
+            self.loss_function.den_override = prev_override
         pred_ = torch.argmax(lp_, 1)
         if train:
             loss.backward()
             optimizer.step()
-        return loss.detach(), pred_, labels_
+        logged = loss.detach()
+        if den is not None:
+            # each rank holds (local numerator / global denominator): the logged value is their sum = the loss of the
+            # whole global batch, identical on every rank (one more scalar all-reduce, recorded with the step)
+            logged = self.grad_reducer.sum_tensor(logged.clone())
+        return logged, pred_, labels_
 
 
 class GraphedTrainStep:
@@ -191,6 +201,14 @@ class GraphedTrainStep:
             out.update(loss=loss, pred=pred, labels=labels)
         return out
 
+    def release(self) -> None:
+        """Drops the recorded graphs (they hold the captured NCCL kernels and the static batches).  Call before
+        tearing the process group down: drop graphs -> synchronize -> destroy group."""
+        self._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def __call__(self, batch: Batch):
         from . import functional as GF
         dev = batch.text.device
@@ -214,10 +232,16 @@ class GraphedTrainStep:
                     with torch.cuda.graph(graph):
                         self.seeds.advance()
                         out = self._body(static)
-                except Exception:
-                    if not self.distributed:
+                except RuntimeError as exc:
+                    # Only a failed *capture* of the collectives is survivable (a backend whose all-reduce cannot be
+                    # recorded): anything else, and any failure without data parallelism, is a real bug and propagates.
+                    msg = str(exc).lower()
+                    if not self.distributed or not any(k in msg for k in ("captur", "nccl", "graph")):
                         raise
-                    self.enabled = False          # this process group cannot be captured: eager from now on
+                    import warnings
+                    warnings.warn(f"GraphedTrainStep: the data-parallel step could not be captured ({exc}); "
+                                  "running eagerly from now on", RuntimeWarning)
+                    self.enabled = False
                     torch.cuda.synchronize(dev)
                     self.seeds.advance()
                     return self._body(batch)

@@ -63,6 +63,14 @@ void ganffn_reset_launch_count(void);
 /* Select the GEMM engine (GANFFN_GEMM_*); returns the previous value. */
 int ganffn_set_gemm_engine(int engine);
 
+/* Deterministic gradient accumulation (the reference pins determinism: train_IEMOCAP.py:46-53).  Off (default): weight
+ * gradients of split-K slices, LayerNorm parameter gradients and bias gradients are accumulated with red.global.add --
+ * fast, order-dependent in the last bits.  On: split-K slices go through partial buffers folded in slice order,
+ * LayerNorm partials are folded in block order by the block that finishes last, bias gradients have a single writer;
+ * two runs from the same state are then bit-identical, provided only one backward pass at a time adds to a gradient
+ * arena (the host side runs the networks serially in this mode).  Returns the previous setting. */
+int ganffn_set_deterministic(int on);
+
 /* Weight-gradient products of ganffn_net_bwd on a library-owned side stream (forked from / joined to `stream` by
  * events; default on).  Returns the previous setting.  bench.py switches it off for its per-kernel roofline leg. */
 int ganffn_set_side_streams(int on);

@@ -108,10 +108,11 @@ def _trainer_worker(rank, world, port, out_path):
             losses.append(stepper(b)["loss"].detach().clone())
         torch.cuda.synchronize()
         flat = torch.cat([p.detach().reshape(-1) for p in ffn.parameters()])
-        return torch.stack(losses), flat, bool(stepper.kernels_per_replay)
+        captured = bool(stepper.kernels_per_replay)
+        stepper.release()
+        return torch.stack(losses), flat, captured
 
-    l_dp, w_dp, captured = run(parallel.shard_batch(glob, world, rank), red, True)
-    dist.all_reduce(l_dp)                           # each rank holds local numerator / global denominator
+    l_dp, w_dp, captured = run(parallel.shard_batch(glob, world, rank), red, True)   # the trainer logs the global loss
     l_one, w_one, _ = run(glob, None, False)
     ok = {"captured_under_dp": captured,
           "loss_step0": bool(torch.allclose(l_dp[0], l_one[0], rtol=1e-4, atol=0)),
@@ -119,9 +120,8 @@ def _trainer_worker(rank, world, port, out_path):
           "weights": float((w_dp - w_one).abs().mean()) < 0.1 * 1e-4}
     if rank == 0:
         torch.save(ok, out_path)
-    dist.barrier()
-    torch.cuda.synchronize()
-    os._exit(0)      # no communicator teardown under live recorded collectives (see bench.py)
+    if not parallel.shutdown():      # graphs released above -> drain -> barrier -> destroy (watchdog inside)
+        os._exit(3)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
