@@ -96,73 +96,142 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _port_trainer(device="cpu"):
+    import torch
+    from gan_ffn_b200 import synthetic
+    from oracle import reference_port as RP
+    nets, ffn = RP.build()
+    if device != "cpu":
+        for m in list(nets.values()) + [ffn]:
+            m.to(device)
+    return RP.PortTrainer(nets, ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=device))
+
+
+def _pin_eval(tr):
+    """Dropout off: modules pinned in eval mode (the loop bodies' .train() calls become no-ops)."""
+    for m in list(tr.nets.values()) + [tr.ffn]:
+        m.eval()
+        m.train = (lambda mod: (lambda mode=True: mod))(m)
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path (oracle/reference_port.py: stock torch modules, the
-    reference's own operators and loop bodies) on the box's host cores.  Each step is a bounded sample of the
-    workload: `--ref-dialogues` dialogues (default 4 of the 32) at the same S=94, so the run ends in minutes."""
+    reference's own operators and loop bodies) on the box's host cores, on the SAME config as our arm: all
+    `--dialogues` (32) dialogues at S=94 per step, dropout on, `--warmup` warm-up steps and `--steps` timed steps.
+    (~10 s per step on 16 cores: 25 steps are ~4 minutes.)  Safety valve only: if the first warm-up step projects the
+    whole run beyond 20 minutes, fewer steps are timed and the line says so."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from gan_ffn_b200 import synthetic
-    from oracle import reference_port as RP
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    nets, ffn = RP.build()
-    tr = RP.PortTrainer(nets, ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS))
-    # bounded sample: CPU step time here is ~1.9 s fixed (Adam, weight traffic) + ~1.0 s per dialogue; pick the
-    # largest dialogue count (<= 32) that keeps warm-up + K steps within ~4 minutes.
-    warm = min(args.warmup, 1)
-    nd = args.ref_dialogues or int(max(2, min(B_IEMOCAP, (240.0 / (args.steps + warm) - 1.9) / 1.0)))
-    b = synthetic.make_batch(n_dialogues=nd, seq_len=S_IEMOCAP)
+    tr = _port_trainer()
+    nd = args.ref_dialogues or args.dialogues
+    b = synthetic.make_batch(n_dialogues=nd, seq_len=args.seq_len)
     def step():
         tr.gan_batch(b)
         tr.classifier_step(b)
-    for _ in range(warm):
+    warm, steps = max(args.warmup, 1), args.steps
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    if first * (warm + steps) > 1200.0:
+        steps = max(1, int(1200.0 / first) - warm) if int(1200.0 / first) > warm else 1
+        warm = min(warm, max(1, int(1200.0 / first) - steps))
+    for _ in range(warm - 1):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
+    # BASELINE.md §3: 59 % of the CPU train time is dropout RNG -- also time the same step with dropout off
+    tr_off = _port_trainer()
+    _pin_eval(tr_off)
+    tr_off.gan_batch(b); tr_off.classifier_step(b)
+    t1 = time.perf_counter()
+    tr_off.gan_batch(b); tr_off.classifier_step(b)
+    dt_off = time.perf_counter() - t1
     slots = b.padded_slots
-    val = slots * args.steps / dt
-    sample = f"{nd} of {B_IEMOCAP} dialogues at S={S_IEMOCAP} ({slots} padded slots/step), {warm} warm-up + {args.steps} steps, dropout on"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+    val = slots * steps / dt
+    sample = (f"all {nd} dialogues at S={args.seq_len} ({slots} padded slots/step), {warm} warm-up + {steps} timed steps, dropout on"
+              + ("" if steps == args.steps else f" (asked for {args.steps} steps: cut to stay within 20 minutes)"))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample, "torch": torch.__version__},
+            "config": {"workload": WORKLOAD if (args.seq_len, nd) == (S_IEMOCAP, B_IEMOCAP) else f"train_step S={args.seq_len} B={nd}",
+                       "seq_len": args.seq_len, "dialogues_per_gpu": nd, "sample": sample, "torch": torch.__version__,
+                       "ms_per_step_dropout_off": 1e3 * dt_off, "value_dropout_off": slots / dt_off,
+                       "dropout_off_note": "one timed step after one warm-up, modules pinned in eval mode (BASELINE.md §3: the CPU train step is dominated by dropout RNG)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(seconds_budget=25.0):
-    """The oracle port timed on the host cores on a bounded sample (rank 0, N=1 only)."""
+def cpu_baseline():
+    """The oracle port timed on the host cores on a bounded sample of the same workload (rank 0, N=1 only): one
+    warm-up and one timed step of the full 32-dialogue batch, dropout on (~10 s each on 16 cores), plus one
+    dropout-off step."""
     import torch
     from gan_ffn_b200 import synthetic
-    from oracle import reference_port as RP
     cores = os.cpu_count() or 1
     prev = torch.get_num_threads()
     torch.set_num_threads(cores)
     try:
-        nets, ffn = RP.build()
-        tr = RP.PortTrainer(nets, ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS))
-        nd = 4
-        b = synthetic.make_batch(n_dialogues=nd, seq_len=S_IEMOCAP)
-        tr.gan_batch(b); tr.classifier_step(b)           # warm-up
+        tr = _port_trainer()
+        b = synthetic.make_batch(n_dialogues=B_IEMOCAP, seq_len=S_IEMOCAP)
+        small = synthetic.make_batch(n_dialogues=2, seq_len=S_IEMOCAP)
+        tr.gan_batch(small); tr.classifier_step(small)           # warm-up (thread pools, allocator) on two dialogues
         t0 = time.perf_counter()
-        n = 0
-        while True:
-            tr.gan_batch(b); tr.classifier_step(b)
-            n += 1
-            if time.perf_counter() - t0 > seconds_budget * 0.5 or n >= 2:
-                break
+        tr.gan_batch(b); tr.classifier_step(b)
         dt = time.perf_counter() - t0
-        return {"value": b.padded_slots * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{n} steps of {nd} of {B_IEMOCAP} dialogues at S={S_IEMOCAP} ({b.padded_slots} slots/step), dropout on, torch {torch.__version__} CPU"}
+        _pin_eval(tr)
+        t1 = time.perf_counter()
+        tr.gan_batch(b); tr.classifier_step(b)
+        dt_off = time.perf_counter() - t1
+        return {"value": b.padded_slots / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "value_dropout_off": b.padded_slots / dt_off,
+                "sample": f"1 step of all {B_IEMOCAP} dialogues at S={S_IEMOCAP} ({b.padded_slots} slots/step) after a 2-dialogue warm-up, "
+                          f"dropout on; value_dropout_off = 1 more step with dropout off; torch {torch.__version__} CPU"}
     finally:
         torch.set_num_threads(prev)
+
+
+def gpu_eager_baseline(dev, steps=3):
+    """SURVEY.md §2a's comparator "the reference on the box": the stock-torch port (nn.TransformerEncoder, cuBLAS,
+    torch SDPA, torch.optim.Adam; the reference's loop bodies) in eager mode on the same B200, same batch, dropout
+    on -- once with fp32 matmuls (allow_tf32=False, the parity-equivalent setting) and once with TF32 allowed."""
+    import torch
+    from gan_ffn_b200 import synthetic
+    out = {}
+    b = synthetic.make_batch(n_dialogues=B_IEMOCAP, seq_len=S_IEMOCAP).to(dev)
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            tr = _port_trainer(dev)
+            for _ in range(2):
+                tr.gan_batch(b); tr.classifier_step(b)
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ms1 = ms2 = 0.0
+            for _ in range(steps):
+                e0.record(); tr.gan_batch(b); e1.record(); tr.classifier_step(b); e2.record()
+                torch.cuda.synchronize()
+                ms1 += e0.elapsed_time(e1); ms2 += e1.elapsed_time(e2)
+            ms = (ms1 + ms2) / steps
+            out[tag] = {"ms_per_step": ms, "stage1_ms": ms1 / steps, "stage2_ms": ms2 / steps, "value": b.padded_slots / (ms / 1e3), "unit": UNIT}
+            del tr
+        out["note"] = ("stock torch eager (oracle/reference_port.py on cuda): cuBLAS SGEMM / TF32 GEMM, torch SDPA, foreach Adam; "
+                       f"{steps} timed steps after 2 warm-ups, CUDA events, same S=94 B=32 batch, dropout on; host-launch bound (~5 k launches per step)")
+        out["torch"] = torch.__version__
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -345,6 +414,12 @@ def run_ours(args):
 
     if rank == 0:
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        eager = None
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                eager = gpu_eager_baseline(dev)
+            except Exception as exc:   # an auxiliary leg must not take the headline down
+                eager = {"error": f"{type(exc).__name__}: {exc}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -364,6 +439,8 @@ def run_ours(args):
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         if hbm is not None:
             line["roofline_hbm"] = hbm
         if graph is not None:
@@ -387,9 +464,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seq-len", type=int, default=S_IEMOCAP)
     ap.add_argument("--dialogues", type=int, default=B_IEMOCAP, help="dialogues per GPU")
-    ap.add_argument("--ref-dialogues", type=int, default=0, help="dialogues per step of the CPU reference arm (0 = fit ~4 min)")
+    ap.add_argument("--ref-dialogues", type=int, default=0, help="dialogues per step of the CPU reference arm (0 = the same as --dialogues)")
     ap.add_argument("--engine", default=None, choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-torch-eager-on-GPU comparator leg")
     ap.add_argument("--no-graph", action="store_true", help="skip the dialogue-graph kernel leg (HBM GB/s of edge build / gathers)")
     ap.add_argument("--graph-utterances", type=int, default=1_000_000)
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")

@@ -141,7 +141,8 @@ class PortTrainer:
     def gan_batch(self, b):
         n, o, adv = self.nets, self.opts, self.adv
         S, B = b.text.size(0), b.text.size(1)
-        valid, fake = torch.ones(S, B, 1), torch.zeros(S, B, 1)
+        dev = b.text.device          # CPU for the baseline legs; bench.py's gpu_eager_baseline leg runs the same port on the GPU
+        valid, fake = torch.ones(S, B, 1, device=dev), torch.zeros(S, B, 1, device=dev)
         t, v, a = b.text, b.visual, b.acoustic
         L = {}
         L["visual_D_loss"] = _train_disc(n["visual_disc"], v, n["acoustic_gen"], a, o["visual_disc"], adv, valid, fake)

@@ -97,3 +97,37 @@ def test_shard_indices_cover_each_dialogue_once():
     b = H.synthetic.make_batch(n_dialogues=6, lengths=[4, 9, 2, 9, 5, 1])
     sh = parallel.shard_batch(b, 4, 1)
     assert sh.seq_len == 9 and sh.lengths == [2, 9] and torch.equal(sh.text, b.text[:, 2:4])
+
+
+def test_data_parallel_wrapped_reference_checkpoints_load():
+    """The reference trains on GPU with every network wrapped in nn.DataParallel and GAN_FFN holding the wrapped
+    generators (train_IEMOCAP.py:587-593, :629-635), and pickles whole modules (:427-438): state_dict keys carry
+    `module.` segments at the top level and nested.  load_reference_state strips them and loads strictly."""
+    import torch.nn as nn
+    import gan_ffn_b200 as GB
+    from gan_ffn_b200 import model as M
+    from oracle import reference_port as RP
+    pnets, _ = RP.build(seed=11)
+    wrapped = {k: nn.DataParallel(v) for k, v in pnets.items()}                      # :587-593
+    pffn = RP.PortGANFFN(wrapped["acoustic_gen"], wrapped["visual_gen"], wrapped["text_gen"], 6, dropout=0.6)   # :629-635
+    keys = list(pffn.state_dict())
+    assert any(k.startswith("acoustic_generator.module.") for k in keys)
+    assert all(k.startswith("module.") for k in wrapped["text_disc"].state_dict())
+
+    torch.manual_seed(5)
+    ours = {"acoustic_gen": M.AcousticGenerator(100), "visual_gen": M.VisualGenerator(100), "text_gen": M.TextGenerator(100),
+            "text_disc": M.TextDiscriminator(100), "visual_disc": M.VisualDiscriminator(100)}
+    ffn = M.GAN_FFN(ours["acoustic_gen"], ours["visual_gen"], ours["text_gen"], n_classes=6, dropout=0.6)
+    with pytest.raises(RuntimeError):
+        ours["text_disc"].load_state_dict(wrapped["text_disc"].state_dict())         # the prefixed keys do not load as is
+    for k in ("text_disc", "visual_disc"):
+        res = GB.load_reference_state(ours[k], wrapped[k])                           # a wrapped module ...
+        assert not res.missing_keys and not res.unexpected_keys
+    res = GB.load_reference_state(ffn, pffn.state_dict())                            # ... or its state_dict, nested wrappers
+    assert not res.missing_keys and not res.unexpected_keys
+    for k in ("acoustic_gen", "visual_gen", "text_gen", "text_disc", "visual_disc"):
+        for (n1, p1), (n2, p2) in zip(sorted(ours[k].state_dict().items()), sorted(pnets[k].state_dict().items())):
+            assert n1 == n2 and torch.equal(p1, p2), (k, n1, n2)
+    assert torch.equal(ffn.fc.weight, pffn.fc.weight)
+    # a plain (unwrapped) checkpoint goes through the same call
+    GB.load_reference_state(ours["text_gen"], pnets["text_gen"].state_dict())
