@@ -255,8 +255,10 @@ def run_ours(args):
     reducer = parallel.GradReducer() if world > 1 else None
     nets, ffn = train.build_networks(device=dev)
     gan = train.GANTrainer(nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], nets["acoustic_disc"],
-                           nets["visual_disc"], nets["text_disc"], grad_reducer=reducer, world_size=world)
-    cls = train.ClassifierTrainer(ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev), grad_reducer=reducer)
+                           nets["visual_disc"], nets["text_disc"], grad_reducer=reducer, world_size=world,
+                           overlap=not args.no_lanes, batch_disc=not args.no_batch_disc)
+    cls = train.ClassifierTrainer(ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev), grad_reducer=reducer,
+                                  overlap=not args.no_lanes)
     G.manual_seed(3407 + rank)
 
     S, B = args.seq_len, args.dialogues
@@ -332,6 +334,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = slots * args.steps / float(t.item())
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "quick": True,
+                              "stage1_ms": stage1_ms, "stage2_ms": stage2_ms, "e2e": e2e_value, "gpu_launches": launches,
+                              "lanes": not args.no_lanes, "batch_disc": not args.no_batch_disc, "clocks": clocks}), flush=True)
+        if world > 1 and not parallel.shutdown([stepper]):
+            os._exit(0)
+        return
+
     # ---- roofline leg: per-GEMM CUDA events over one more step ------------------------------------------------------
     # every kernel alone on the device for this leg: network lanes and the weight-gradient side stream off, otherwise
     # an event bracket also measures the time its kernel spends sharing SMs with other streams' kernels
@@ -347,7 +359,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     L.cdll.ganffn_gemm_profile_enable(0)
     L.cdll.ganffn_set_side_streams(prev_side)
-    gan.overlap, cls.overlap = True, True
+    gan.overlap, cls.overlap = not args.no_lanes, not args.no_lanes
     ms_a, fl_a, n_a = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     L.call("ganffn_gemm_profile_collect", 0, ctypes.byref(ms_a), ctypes.byref(fl_a), ctypes.byref(n_a))
     gemm_ms, gemm_flops, gemm_n = ms_a.value, fl_a.value, n_a.value
@@ -470,6 +482,9 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-torch-eager-on-GPU comparator leg")
     ap.add_argument("--no-graph", action="store_true", help="skip the dialogue-graph kernel leg (HBM GB/s of edge build / gathers)")
     ap.add_argument("--graph-utterances", type=int, default=1_000_000)
+    ap.add_argument("--no-lanes", action="store_true", help="A/B switch: run the networks of a loop body serially (no concurrent lanes)")
+    ap.add_argument("--no-batch-disc", action="store_true", help="A/B switch: train_disc as two discriminator passes (reference body) instead of one [real|fake] pass")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e only: skip the roofline, Adam, graph, CPU and eager-GPU legs (A/B runs)")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()
     if args.impl == "reference":

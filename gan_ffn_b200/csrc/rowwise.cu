@@ -211,10 +211,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
   __threadfence();
   __syncthreads();
-  __shared__ unsigned ticket;
-  if (threadIdx.x == 0) ticket = atomicAdd(&g_ln_counter, 1u);
-  __syncthreads();
-  if (ticket != gridDim.x - 1) return;
+  // (no static __shared__ here: at d = 512 the dynamic buffer already is the whole 48 KB default limit)
+  const unsigned ticket = threadIdx.x == 0 ? atomicAdd(&g_ln_counter, 1u) : 0u;
+  if (!__syncthreads_or(threadIdx.x == 0 && ticket == gridDim.x - 1)) return;
   __threadfence();
   for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
     const int seg = c / d;

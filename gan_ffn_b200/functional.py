@@ -404,6 +404,73 @@ def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Ten
 
 
 # --------------------------------------------------------------------------------------
+# a single nn.Linear whose parameters live in a network arena (VisualDiscriminator.object, model.py:1344, 1355-1356)
+# --------------------------------------------------------------------------------------
+class _ArenaLinearFunction(torch.autograd.Function):
+    """y = x W^T + b with W, b at offsets (ow, ob) of ``arena``; the weight / bias gradients are accumulated straight
+    into the arena's gradient buffer (like _NetFunction).  Used when the `object` projection of the visual
+    discriminator has to run on its own: the batched real|fake pass of ``train_disc_batched`` projects only the
+    real half."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, arena: ParamArena, ow: int, ob: int, n_out: int):
+        L = lib()
+        S, B, K = x.shape
+        M = S * B
+        y = torch.empty((S, B, n_out), dtype=torch.float32, device=x.device)
+        nsc = L.query("ganffn_gemm_scratch_floats", M, n_out, K)
+        ws = scratch(x.device, nsc, _scratch_tag(x.device) + "/lin")
+        _call(x, "ganffn_linear_fwd", ptr(x), arena.flat.data_ptr() + 4 * ow, arena.flat.data_ptr() + 4 * ob, None, ptr(y),
+              None, M, n_out, K, 0, 0, 0.0, 0, 0, ptr(ws), nsc, _stream(x))
+        ctx.arena, ctx.ow, ctx.ob, ctx.n_out = arena, ow, ob, n_out
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        (x,), arena = ctx.saved_tensors, ctx.arena
+        S, B, K = x.shape
+        M = S * B
+        dy = dy.contiguous()
+        cur = torch.cuda.current_stream(x.device)
+        if _lanes.streams and _lanes.is_lane(cur.cuda_stream):
+            _lanes.touch(cur)
+        if not arena.grads_live():
+            if not arena.prezeroed:
+                arena.grad.zero_()
+                arena.zero_event = torch.cuda.Event()
+                arena.zero_event.record(cur)
+                arena.zero_stream = cur.cuda_stream
+            arena.prezeroed = False
+            arena.install_grads()
+        elif arena.zero_event is not None and arena.zero_stream != cur.cuda_stream:
+            cur.wait_event(arena.zero_event)
+        nsc = L.query("ganffn_wgrad_scratch_floats", M, ctx.n_out, K)
+        ws = scratch(x.device, nsc, _scratch_tag(x.device) + "/lin")
+        _call(x, "ganffn_linear_wgrad", ptr(dy), ptr(x), arena.grad.data_ptr() + 4 * ctx.ow,
+              arena.grad.data_ptr() + 4 * ctx.ob, M, ctx.n_out, K, 1, ptr(ws), _stream(x))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            nsd = L.query("ganffn_gemm_scratch_floats", M, K, ctx.n_out)
+            wsd = scratch(x.device, nsd, _scratch_tag(x.device) + "/lin")
+            _call(x, "ganffn_linear_dgrad", ptr(dy), arena.flat.data_ptr() + 4 * ctx.ow, None, ptr(dx), M, ctx.n_out, K,
+                  ptr(wsd), nsd, _stream(x))
+        return dx, None, None, None, None, None
+
+
+def arena_linear(x: torch.Tensor, arena: ParamArena, ow: int, ob: int, n_out: int) -> torch.Tensor:
+    _require_cuda(x, "linear input")
+    x = x.contiguous()
+    anchor = arena.flat
+    if arena.requires_grad and torch.is_grad_enabled():
+        anchor = arena.flat.detach().requires_grad_(True)
+    _lanes.join()          # runs on the caller's stream: inputs made on lanes must have landed
+    return _ArenaLinearFunction.apply(x, anchor, arena, ow, ob, n_out)
+
+
+# --------------------------------------------------------------------------------------
 # fusion + classifier + log-softmax   (GAN_FFN.forward, model.py:1444-1449)
 # --------------------------------------------------------------------------------------
 class _FuseClsFunction(torch.autograd.Function):

@@ -170,6 +170,18 @@ class _Discriminator(_FusedNet):
         self.dropout = nn.Dropout(dropout)
 
 
+    def project_real(self, real: torch.Tensor) -> torch.Tensor:
+        """What ``forward`` does to a *real* feature before the positional encoding: the identity, except for the
+        visual discriminator whose 512-wide real input goes through ``object`` (model.py:1355-1356).  Used by the
+        batched real|fake pass of ``train.train_disc_batched``."""
+        obj = getattr(self, "object", None)
+        if obj is None or real.size(-1) != obj.in_features:
+            return real
+        ar = self.arena()
+        tab = ar.table
+        return GF.arena_linear(real, ar, int(tab[-2]), int(tab[-1]), obj.out_features)
+
+
 class AcousticDiscriminator(_Discriminator):
     """fusion (seq_len, batch, D_h) -> prob (seq_len, batch, 1).  reference model.py:1297-1327."""
 

@@ -41,6 +41,29 @@ def train_disc(disc, real_dics, gen, real_gen, opt, adversarial_loss, valid, fak
     return res
 
 
+def train_disc_batched(disc, real_dics, gen, real_gen, opt, adversarial_loss, valid, fake):
+    """``train_disc`` with the discriminator's two passes (real features, generated features: the same weights) run
+    as ONE pass over 2B dialogues:  prob = D([real | G(x).detach()]) and
+    (BCE(prob_real, 1) + BCE(prob_fake, 0)) / 2 == BCE(prob, [1 | 0]) because both halves have S*B slots.
+    Same losses, gradients and update as reference train_IEMOCAP.py:200-227 (dialogues do not interact; only the
+    dropout-mask stream and the fp32 summation order differ); every kernel of the discriminator sees M = 2*S*B rows,
+    so the d=100 products launch twice the CTAs for the same fixed per-launch cost."""
+    disc.train()
+    gen.eval()
+
+    opt.zero_grad()
+    fusion = gen(real_gen)
+    real_in = disc.project_real(real_dics)               # `object` 512 -> 100 for real visual features (model.py:1355)
+    GF.join_lanes()                                       # torch.cat is a plain torch op on the caller's stream
+    both = torch.cat([real_in, fusion.detach()], dim=1)   # (S, 2B, D_h): dialogues side by side, global pad length kept
+    prob = disc(both)
+    d_loss = adversarial_loss(prob, torch.cat([valid, fake], dim=1))
+    res = d_loss.detach()
+    d_loss.backward()
+    opt.step()
+    return res
+
+
 def train_gen(gen, real_gen, disc, opt, adversarial_loss, valid, fake):
     """reference train_IEMOCAP.py:230-252."""
     gen.train()
@@ -61,7 +84,7 @@ class GANTrainer:
     optimizers (generators lr, discriminators lr/2, text generator lr*1.1), BCE adversarial loss."""
 
     def __init__(self, acoustic_gen, visual_gen, text_gen, acoustic_disc, visual_disc, text_disc, lr=GAN_LR, b1=GAN_B1,
-                 b2=GAN_B2, grad_reducer=None, world_size: int = 1, overlap: bool = True):
+                 b2=GAN_B2, grad_reducer=None, world_size: int = 1, overlap: bool = True, batch_disc: bool = True):
         self.nets = dict(acoustic_gen=acoustic_gen, visual_gen=visual_gen, text_gen=text_gen, acoustic_disc=acoustic_disc,
                          visual_disc=visual_disc, text_disc=text_disc)
         mk = lambda net, rate: FusedAdam(net, lr=rate, betas=(b1, b2), grad_reducer=grad_reducer)
@@ -75,6 +98,8 @@ class GANTrainer:
         self.grad_reducer, self.world_size = grad_reducer, world_size
         # independent networks of a sub-step on concurrent streams (functional._Lanes); the loop bodies are unchanged
         self.overlap = overlap
+        # train_disc as one discriminator pass over [real | fake] (train_disc_batched) instead of two
+        self.batch_disc = batch_disc
 
     def batch(self, data: Batch) -> Dict[str, torch.Tensor]:
         """The twelve sub-steps of one batch, in the reference's order (train_IEMOCAP.py:355-382).
@@ -98,6 +123,7 @@ class GANTrainer:
         if self.grad_reducer is not None:
             adv.scale_tensor = self.grad_reducer.local_fraction_tensor(batch_size, real_text.device)
         loss = {}
+        train_disc = train_disc_batched if self.batch_disc else globals()["train_disc"]
         loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["acoustic_gen"], real_acoustic, self.opt_visual_D, adv, valid, fake)
         loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["visual_disc"], self.opt_acoustic_G, adv, valid, fake)
         loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["text_gen"], real_text, self.opt_visual_D, adv, valid, fake)

@@ -87,11 +87,15 @@ def _compare_updates(name, ours_before, ours_after, port_before, port_after, lr,
     assert stats["max_err_over_lr"] <= steps * 2.0 * 1.001, stats
 
 
+@pytest.mark.parametrize("batch_disc", [False, True], ids=["two-pass-disc", "batched-disc"])
 @pytest.mark.parametrize("overlap", [False, True], ids=["serial", "lanes"])
-def test_gan_batch_and_classifier_step_match_reference_port(overlap):
+def test_gan_batch_and_classifier_step_match_reference_port(overlap, batch_disc):
+    """batch_disc=False is the reference's train_disc body verbatim (two discriminator passes); True runs them as one
+    pass over [real | fake] (train.train_disc_batched) -- both must match the port."""
     from gan_ffn_b200 import synthetic
     nets, ffn, gan, cls, pnets, pffn, port = _build_pair()
     gan.overlap = cls.overlap = overlap
+    gan.batch_disc = batch_disc
     batch = synthetic.make_batch(n_dialogues=4, lengths=[14, 9, 12, 5], seed=11)
     cb = batch.to("cuda")
 
@@ -105,7 +109,7 @@ def test_gan_batch_and_classifier_step_match_reference_port(overlap):
     assert sorted(ours) == sorted(ref) == LOSS_KEYS, "the six surviving loss keys of train_IEMOCAP.py:355-382"
     for k in LOSS_KEYS:
         a, e = float(ours[k]), float(ref[k])
-        _log(f"PARITY trainer-loss {k} ours={a:.8f} port={e:.8f} rel={abs(a - e) / abs(e):.2e} overlap={overlap}")
+        _log(f"PARITY trainer-loss {k} ours={a:.8f} port={e:.8f} rel={abs(a - e) / abs(e):.2e} overlap={overlap} batch_disc={batch_disc}")
         assert abs(a - e) <= H.RTOL * abs(e), (k, a, e)
     torch.cuda.synchronize()
     for k in nets:
