@@ -358,57 +358,67 @@ __device__ __forceinline__ void store_row(float* g, const float* acc, float mul)
   }
 }
 
+// q (registers) . row (registers)
 template <int HD>
-__global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_fwd_small_kernel(const float* __restrict__ qkv,
-                                                                               float* __restrict__ o, float* __restrict__ lse,
-                                                                               int S, int B, int d, int nhead, float p_drop,
-                                                                               const Seed seed_ref, uint32_t site) {
+__device__ __forceinline__ float dot_regs(const float* a, const float* b) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < HD; ++c) s = fmaf(a[c], b[c], s);
+  return s;
+}
+
+// One CTA = (dialogue, head, block of 32 rows), four warps = four groups.  r2: the (dialogue, head) CTAs of the first
+// version held 384 threads / 110 KB and ran two per SM, so the 320 CTAs of an S=94, B=32 layer took two waves on 296
+// slots (the second with 24 CTAs): 24.7 / 37.4 us for 5.9 / 12 us of issue time.  With 32-row CTAs of 128 threads
+// (7.5 - 16 KB of shared memory) 960 CTAs are all resident at once and nothing is quantised.
+template <int HD>
+__global__ void __launch_bounds__(NG * 32, 5) attention_fwd_small_kernel(const float* __restrict__ qkv,
+                                                                        float* __restrict__ o, float* __restrict__ lse,
+                                                                        int S, int B, int d, int nhead, float p_drop,
+                                                                        const Seed seed_ref, uint32_t site) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PW = HD | 1;         // odd row stride of the partial rows (lane = row: conflict-free)
-  float* Qs = smem;                  // [S][HD]
-  float* Ks = Qs + S * HD;
+  float* Ks = smem;                  // [S][HD]
   float* Vs = Ks + S * HD;
-  float* redm = Vs + S * HD;         // [NG][S] partial row max
-  float* reds = redm + NG * S;       // [NG][S] partial row sums
-  float* part = reds + NG * S;       // [NG-1][S][PW] partial P V rows of groups 1..NG-1
-  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  float* redm = Vs + S * HD;         // [NG][32] partial row max
+  float* reds = redm + NG * 32;      // [NG][32] partial row sums
+  float* part = reds + NG * 32;      // [NG-1][32][PW] partial P V rows of groups 1..NG-1
+  const int nrw = (S + 31) >> 5;
+  const int bh = blockIdx.x / nrw, rw = blockIdx.x % nrw;
+  const int b = bh / nhead, h = bh % nhead;
   const int ld = B * 3 * d;
   const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
-  load_tile<HD>(base, ld, Qs, S);
   load_tile<HD>(base + d, ld, Ks, S);
   load_tile<HD>(base + 2 * d, ld, Vs, S);
-  __syncthreads();
 
-  const int nrw = (S + 31) >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = warp / nrw, i = (warp % nrw) * 32 + lane;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = rw * 32 + lane;
   const bool active = i < S;
   const int ir = active ? i : S - 1;
   const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;
   const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
   const float scale = rsqrtf((float)HD);
+  float q[HD];
+  row_to_regs<HD>(base + (size_t)ir * ld, q, scale);   // the thread's own query row straight from global memory
+  __syncthreads();
 
   float s[KPG];
   float mx = -INFINITY;
-  {
-    float q[HD];
-    row_to_regs<HD>(Qs + ir * HD, q, scale);
 #pragma unroll
-    for (int k = 0; k < KPG; ++k) {
-      const int j = j_beg + k;
-      s[k] = (j < j_end) ? dot_smem<HD>(q, Ks + j * HD) : -INFINITY;
-      mx = fmaxf(mx, s[k]);
-    }
+  for (int k = 0; k < KPG; ++k) {
+    const int j = j_beg + k;
+    s[k] = (j < j_end) ? dot_smem<HD>(q, Ks + j * HD) : -INFINITY;
+    mx = fmaxf(mx, s[k]);
   }
-  redm[g * S + ir] = mx;
+  redm[g * 32 + lane] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(redm[ir], redm[S + ir]), fmaxf(redm[2 * S + ir], redm[3 * S + ir]));
+  mx = fmaxf(fmaxf(redm[lane], redm[32 + lane]), fmaxf(redm[64 + lane], redm[96 + lane]));
 
   const bool drop = p_drop > 0.f;
   const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int S4 = (S + 3) & ~3;
-  const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
+  const uint64_t ebase = ((uint64_t)bh * S + ir) * S4;
   float lsum = 0.f;
   float acc[HD];
 #pragma unroll
@@ -429,46 +439,53 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_fwd_small_kerne
       }
     }
   }
-  reds[g * S + ir] = lsum;
+  reds[g * 32 + lane] = lsum;
   if (g > 0) {
-    float* pr = part + ((size_t)(g - 1) * S + ir) * PW;
+    float* pr = part + ((size_t)(g - 1) * 32 + lane) * PW;
 #pragma unroll
     for (int c = 0; c < HD; ++c) pr[c] = acc[c];
   }
   __syncthreads();
   if (g == 0 && active) {
-    lsum = (reds[i] + reds[S + i]) + (reds[2 * S + i] + reds[3 * S + i]);
+    lsum = (reds[lane] + reds[32 + lane]) + (reds[64 + lane] + reds[96 + lane]);
 #pragma unroll
     for (int gg = 0; gg < NG - 1; ++gg) {
-      const float* pr = part + ((size_t)gg * S + i) * PW;
+      const float* pr = part + ((size_t)gg * 32 + lane) * PW;
 #pragma unroll
       for (int c = 0; c < HD; ++c) acc[c] += pr[c];
     }
     store_row<HD>(o + ((size_t)i * B + b) * d + (size_t)h * HD, acc, 1.f / lsum);
-    lse[(size_t)blockIdx.x * S + i] = mx + logf(lsum);
+    lse[(size_t)bh * S + i] = mx + logf(lsum);
   }
 }
 
-//   lane = query i, group = key range:   P_ij, dP_ij, Ps = P m, dSs = P (dP m - D_i) scale   (registers + smem)
-//                                        dQ_i partial = sum_{j in range} dSs_ij k_j            (registers)
-//   lane = key j,   group = query range: dV_j partial = sum_i Ps_ij dO_i,  dK_j partial = sum_i dSs_ij q_i
+// Backward, same CTA shape, no S x S matrix anywhere: the probabilities are recomputed in both sweeps.
+//   sweep A  lane = query i of the CTA's row block, group = key range:
+//              P_ij = exp(q_i.k_j - lse_i), dP_ij = dO_i.v_j, dS_ij = P_ij (dP_ij m_ij - D_i) scale;  dQ_i += dS_ij k_j
+//   sweep B  lane = key j of the CTA's row block, group = query range: the same P_ij / dS_ij from the key's side;
+//              dV_j += P_ij m_ij dO_i,  dK_j += dS_ij q_i
+// Recomputing costs ~45 % more instructions than reading an S x S matrix back, but the first version's 110 KB of shared
+// memory per (dialogue, head) CTA is what capped it at two CTAs per SM (see the forward kernel).  Dropout bits in
+// sweep B: one 64-bit word covers four consecutive keys of one query, i.e. four neighbouring lanes; for a chunk of four
+// queries each lane generates the word of query (lane & 3) of its key quad and the quad exchanges them by shuffle.
 template <int HD>
-__global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_bwd_small_kernel(
+__global__ void __launch_bounds__(NG * 32, 5) attention_bwd_small_kernel(
     const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
     const float* __restrict__ d_o, float* __restrict__ dqkv, int S, int B, int d, int nhead, float p_drop,
     const Seed seed_ref, uint32_t site) {
   extern __shared__ __align__(16) float smem[];
-  const int SP = S | 1;
   constexpr int PW = (2 * HD) | 1;
   float* Qs = smem;                 // [S][HD]
   float* Ks = Qs + S * HD;
   float* Vs = Ks + S * HD;
   float* dOs = Vs + S * HD;
-  float* Ps = dOs + S * HD;         // [S][SP] dropped, scaled probabilities
-  float* dSs = Ps + S * SP;         // [S][SP]
-  float* part = dSs + S * SP;       // [NG-1][S][PW] partial rows: first dQ (HD wide), later dV | dK (2 HD wide)
+  float* Ls = dOs + S * HD;         // [S] row log-sum-exp
+  float* Ds = Ls + S;               // [S] rowsum(dO * O)
+  float* part = Ds + S;             // [NG-1][32][PW] partial rows: dQ (HD wide), later dV | dK (2 HD wide)
 
-  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  const int nrw = (S + 31) >> 5;
+  const int bh = blockIdx.x / nrw, rw = blockIdx.x % nrw;
+  const int b = bh / nhead, h = bh % nhead;
   const int ld = B * 3 * d;
   const int ldo = B * d;
   const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
@@ -478,10 +495,17 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_bwd_small_kerne
   load_tile<HD>(base + d, ld, Ks, S);
   load_tile<HD>(base + 2 * d, ld, Vs, S);
   load_tile<HD>(dobase, ldo, dOs, S);
+  for (int r = threadIdx.x; r < S; r += blockDim.x) {
+    float orow[HD], drow[HD];
+    row_to_regs<HD>(obase + (size_t)r * ldo, orow, 1.f);
+    row_to_regs<HD>(dobase + (size_t)r * ldo, drow, 1.f);
+    Ds[r] = dot_regs<HD>(drow, orow);
+    Ls[r] = lse[(size_t)bh * S + r];
+  }
+  __syncthreads();
 
-  const int nrw = (S + 31) >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = warp / nrw, i = (warp % nrw) * 32 + lane;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = rw * 32 + lane;       // the thread's row: a query in sweep A, a key in sweep B
   const bool active = i < S;
   const int ir = active ? i : S - 1;
   const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;
@@ -491,82 +515,88 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_bwd_small_kerne
   const uint64_t seed = drop ? seed_value(seed_ref) : 0ull;
   const float dscale = drop ? 1.f / (1.f - p_drop) : 1.f;
   const int S4 = (S + 3) & ~3;
-  const uint64_t ebase = ((uint64_t)blockIdx.x * S + ir) * S4;
-  const float li = lse[(size_t)blockIdx.x * S + ir];
-  float orow[HD];   // this thread's O row straight from global memory (only D_i needs it)
-  {
-    constexpr int W = Cfg<HD>::W;
-    const float* src = obase + (size_t)ir * ldo;
-#pragma unroll
-    for (int c = 0; c < HD; c += W) {
-      if (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(src + c)); orow[c] = v.x; orow[c + 1] = v.y; orow[c + 2] = v.z; orow[c + 3] = v.w; }
-      else if (W == 2) { const float2 v = __ldg(reinterpret_cast<const float2*>(src + c)); orow[c] = v.x; orow[c + 1] = v.y; }
-      else orow[c] = __ldg(src + c);
-    }
-  }
-  __syncthreads();
+  float* out = dqkv + ((size_t)ir * B + b) * 3 * d + (size_t)h * HD;
 
-  float acc[HD];
-#pragma unroll
-  for (int c = 0; c < HD; ++c) acc[c] = 0.f;
+  // ---- sweep A: dQ ----
   {
-    float q[HD], r[HD];
+    float acc[HD], q[HD], r[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = 0.f;
     row_to_regs<HD>(Qs + ir * HD, q, scale);
     row_to_regs<HD>(dOs + ir * HD, r, 1.f);
-    float Di = 0.f;
+    const float Di = Ds[ir], li = Ls[ir];
+    const uint64_t ebase = ((uint64_t)bh * S + ir) * S4;
+    for (int j0 = j_beg; j0 < j_end; j0 += 4) {
+      float msk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop) dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
 #pragma unroll
-    for (int c = 0; c < HD; ++c) Di = fmaf(r[c], orow[c], Di);
-#pragma unroll
-    for (int k4 = 0; k4 < KPG; k4 += 4) {
-      const int j0 = j_beg + k4;
-      if (j0 < j_end) {
-        float msk[4] = {1.f, 1.f, 1.f, 1.f};
-        if (drop) dropout_scale4(seed, site, ebase + j0, p_drop, dscale, msk);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + u;
-          if (j < j_end) {
-            const float pj = expf(dot_smem<HD>(q, Ks + j * HD) - li);
-            const float dpd = dot_smem<HD>(r, Vs + j * HD);
-            const float ds = pj * (dpd * msk[u] - Di) * scale;
-            if (active) {
-              Ps[i * SP + j] = pj * msk[u];
-              dSs[i * SP + j] = ds;
-            }
-            axpy_row<HD>(ds, Ks + j * HD, acc);   // dQ_i partial
-          }
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j < j_end) {
+          const float pj = expf(dot_smem<HD>(q, Ks + j * HD) - li);
+          const float dpd = dot_smem<HD>(r, Vs + j * HD);
+          axpy_row<HD>(pj * (dpd * msk[u] - Di) * scale, Ks + j * HD, acc);
         }
+      }
+    }
+    if (g > 0) {
+      float* pr = part + ((size_t)(g - 1) * 32 + lane) * PW;
+#pragma unroll
+      for (int c = 0; c < HD; ++c) pr[c] = acc[c];
+    }
+    __syncthreads();
+    if (g == 0 && active) {
+#pragma unroll
+      for (int gg = 0; gg < NG - 1; ++gg) {
+        const float* pr = part + ((size_t)gg * 32 + lane) * PW;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) acc[c] += pr[c];
+      }
+      store_row<HD>(out, acc, 1.f);
+    }
+    __syncthreads();   // the partial rows are rewritten by sweep B
+  }
+
+  // ---- sweep B: dV, dK ----
+  float kj[HD], vj[HD], accv[HD], acck[HD];
+  row_to_regs<HD>(Ks + ir * HD, kj, scale);   // scaled once here: P_ij = exp((k_j scale).q_i - lse_i)
+  row_to_regs<HD>(Vs + ir * HD, vj, 1.f);
+#pragma unroll
+  for (int c = 0; c < HD; ++c) { accv[c] = 0.f; acck[c] = 0.f; }
+  const uint64_t key = drop ? drop_key(seed, site) : 0ull;
+  const uint32_t thr = drop ? drop_threshold(p_drop) : 0u;
+  const uint32_t wq = (uint32_t)(ir >> 2);           // the key quad's word within a query's mask row
+  const uint32_t sh = 16u * (uint32_t)(ir & 3);
+  const uint32_t words_per_row = (uint32_t)(S4 >> 2);
+  for (int i0 = j_beg; i0 < j_end; i0 += 4) {
+    uint32_t wlo = 0u, whi = 0u;
+    if (drop) {
+      const int iq = min(i0 + (lane & 3), S - 1);
+      const uint64_t w = drop_word(key, ((uint64_t)bh * S + iq) * words_per_row + wq);
+      wlo = (uint32_t)w; whi = (uint32_t)(w >> 32);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int qi = i0 + u;          // warp-uniform
+      float m = 1.f;
+      if (drop) {
+        const uint32_t lo = __shfl_sync(0xffffffffu, wlo, (lane & ~3) | u);
+        const uint32_t hi = __shfl_sync(0xffffffffu, whi, (lane & ~3) | u);
+        const uint64_t w = ((uint64_t)hi << 32) | lo;
+        m = ((uint32_t)(w >> sh) & 0xFFFFu) >= thr ? dscale : 0.f;
+      }
+      if (qi < j_end) {
+        const float* qrow = Qs + qi * HD;
+        const float* drow = dOs + qi * HD;
+        const float p = expf(dot_smem<HD>(kj, qrow) - Ls[qi]);
+        const float dpd = dot_smem<HD>(vj, drow);
+        axpy_row<HD>(p * m, drow, accv);
+        axpy_row<HD>(p * (dpd * m - Ds[qi]) * scale, qrow, acck);
       }
     }
   }
   if (g > 0) {
-    float* pr = part + ((size_t)(g - 1) * S + ir) * PW;
-#pragma unroll
-    for (int c = 0; c < HD; ++c) pr[c] = acc[c];
-  }
-  __syncthreads();
-  float* out = dqkv + ((size_t)ir * B + b) * 3 * d + (size_t)h * HD;
-  if (g == 0 && active) {
-#pragma unroll
-    for (int gg = 0; gg < NG - 1; ++gg) {
-      const float* pr = part + ((size_t)gg * S + i) * PW;
-#pragma unroll
-      for (int c = 0; c < HD; ++c) acc[c] += pr[c];
-    }
-    store_row<HD>(out, acc, 1.f);
-  }
-  // lane = key j (= ir), group = query range [j_beg, j_end)
-  float accv[HD], acck[HD];
-#pragma unroll
-  for (int c = 0; c < HD; ++c) { accv[c] = 0.f; acck[c] = 0.f; }
-  for (int r = j_beg; r < j_end; ++r) {
-    const float pv = Ps[r * SP + ir], dv = dSs[r * SP + ir];
-    axpy_row<HD>(pv, dOs + r * HD, accv);
-    axpy_row<HD>(dv, Qs + r * HD, acck);
-  }
-  __syncthreads();   // every read of the dQ partials is done: the region is reused for dV | dK
-  if (g > 0) {
-    float* pr = part + ((size_t)(g - 1) * S + ir) * PW;
+    float* pr = part + ((size_t)(g - 1) * 32 + lane) * PW;
 #pragma unroll
     for (int c = 0; c < HD; ++c) { pr[c] = accv[c]; pr[HD + c] = acck[c]; }
   }
@@ -574,7 +604,7 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32, 2) attention_bwd_small_kerne
   if (g == 0 && active) {
 #pragma unroll
     for (int gg = 0; gg < NG - 1; ++gg) {
-      const float* pr = part + ((size_t)gg * S + i) * PW;
+      const float* pr = part + ((size_t)gg * 32 + lane) * PW;
 #pragma unroll
       for (int c = 0; c < HD; ++c) { accv[c] += pr[c]; acck[c] += pr[HD + c]; }
     }
@@ -589,9 +619,8 @@ template <int HD>
 int launch_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed, int site,
                cudaStream_t st) {
   if constexpr (HD <= 16) {
-    auto bytes = [](int s) { return ((size_t)3 * s * HD + (size_t)2 * NG * s + (size_t)(NG - 1) * s * (HD | 1)) * sizeof(float); };
-    GANFFN_SMEM_OPTIN(attention_fwd_small_kernel<HD>, bytes(GANFFN_MAX_SEQ));
-    attention_fwd_small_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
+    auto bytes = [](int s) { return ((size_t)2 * s * HD + (size_t)2 * NG * 32 + (size_t)(NG - 1) * 32 * (HD | 1)) * sizeof(float); };
+    attention_fwd_small_kernel<HD><<<B * nhead * ((S + 31) / 32), NG * 32, bytes(S), st>>>(qkv, o, lse, S, B, d, nhead, p, seed, (uint32_t)site);
     GANFFN_LAUNCHED("attention_fwd_small_kernel");
     return GANFFN_OK;
   } else {
@@ -607,10 +636,9 @@ template <int HD>
 int launch_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
                int nhead, float p, Seed seed, int site, cudaStream_t st) {
   if constexpr (HD <= 16) {
-    auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s * (s | 1) + (size_t)(NG - 1) * s * ((2 * HD) | 1)) * sizeof(float); };
-    GANFFN_SMEM_OPTIN(attention_bwd_small_kernel<HD>, bytes(GANFFN_MAX_SEQ));
-    attention_bwd_small_kernel<HD><<<B * nhead, att_threads(S), bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
-                                                                               (uint32_t)site);
+    auto bytes = [](int s) { return ((size_t)4 * s * HD + (size_t)2 * s + (size_t)(NG - 1) * 32 * ((2 * HD) | 1)) * sizeof(float); };
+    attention_bwd_small_kernel<HD><<<B * nhead * ((S + 31) / 32), NG * 32, bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p,
+                                                                                          seed, (uint32_t)site);
     GANFFN_LAUNCHED("attention_bwd_small_kernel");
     return GANFFN_OK;
   } else {

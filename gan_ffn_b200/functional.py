@@ -125,11 +125,9 @@ _scratch_retired: List[torch.Tensor] = []
 
 
 def _scratch_tag(device: torch.device) -> str:
-    """One workspace per stream: networks on different lanes run concurrently."""
-    if not _lanes.streams:
-        return "main"
+    """One workspace per stream: networks on different lanes / sub-step chains run concurrently."""
     h = torch.cuda.current_stream(device).cuda_stream
-    return f"s{h}" if _lanes.is_lane(h) else "main"
+    return f"s{h}" if h else "main"
 
 
 def scratch(device: torch.device, floats: int, tag: str = "main") -> torch.Tensor:
@@ -169,17 +167,22 @@ class _Lanes:
     def __init__(self):
         self.active = False
         self.n = 3
-        self.streams: Dict[int, List[torch.cuda.Stream]] = {}
+        self.streams: Dict[Tuple[int, int], List[torch.cuda.Stream]] = {}
         self.busy: Dict[int, torch.cuda.Stream] = {}
         self.producers: Dict[int, Tuple[torch.cuda.Event, torch.cuda.Stream]] = {}
         self.counter = 0
+        self.chain_handles = set()      # streams registered as sub-step chains (register_chain_stream)
 
     def lane(self, device: torch.device) -> Tuple[int, torch.cuda.Stream]:
+        """Next lane of the pool that belongs to the caller's current stream: sub-step chains (train.GANTrainer) each
+        fork their own lanes, so kernels of concurrent chains never queue behind each other on a shared lane."""
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        pool = self.streams.get(idx)
+        h = torch.cuda.current_stream(device).cuda_stream
+        key = (idx, h if h in self.chain_handles else 0)   # one shared pool for every non-chain caller stream
+        pool = self.streams.get(key)
         if pool is None:
             pool = [torch.cuda.Stream(device=device) for _ in range(self.n)]
-            self.streams[idx] = pool
+            self.streams[key] = pool
         k = self.counter % self.n
         self.counter += 1
         return k, pool[k]
@@ -226,6 +229,11 @@ class overlap_networks:
 
 def join_lanes() -> None:
     _lanes.join()
+
+
+def register_chain_stream(stream: torch.cuda.Stream) -> None:
+    """Marks ``stream`` as a sub-step chain: networks called on it fork their own pool of lanes."""
+    _lanes.chain_handles.add(stream.cuda_stream)
 
 
 _deterministic = {"on": False}

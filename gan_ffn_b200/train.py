@@ -84,7 +84,8 @@ class GANTrainer:
     optimizers (generators lr, discriminators lr/2, text generator lr*1.1), BCE adversarial loss."""
 
     def __init__(self, acoustic_gen, visual_gen, text_gen, acoustic_disc, visual_disc, text_disc, lr=GAN_LR, b1=GAN_B1,
-                 b2=GAN_B2, grad_reducer=None, world_size: int = 1, overlap: bool = True, batch_disc: bool = True):
+                 b2=GAN_B2, grad_reducer=None, world_size: int = 1, overlap: bool = True, batch_disc: bool = True,
+                 chains: int = 2):
         self.nets = dict(acoustic_gen=acoustic_gen, visual_gen=visual_gen, text_gen=text_gen, acoustic_disc=acoustic_disc,
                          visual_disc=visual_disc, text_disc=text_disc)
         mk = lambda net, rate: FusedAdam(net, lr=rate, betas=(b1, b2), grad_reducer=grad_reducer)
@@ -100,6 +101,9 @@ class GANTrainer:
         self.overlap = overlap
         # train_disc as one discriminator pass over [real | fake] (train_disc_batched) instead of two
         self.batch_disc = batch_disc
+        # independent sub-steps on concurrent chains (see _batch); 1 = the reference's strictly serial order
+        self.chains = chains
+        self._chain_streams = {}
 
     def batch(self, data: Batch) -> Dict[str, torch.Tensor]:
         """The twelve sub-steps of one batch, in the reference's order (train_IEMOCAP.py:355-382).
@@ -108,9 +112,21 @@ class GANTrainer:
         with GF.overlap_networks(self.overlap):
             return self._batch(data)
 
+    # The twelve sub-steps of train_IEMOCAP.py:355-382 in the reference's order: (kind, discriminator, generator, loss key).
+    SUBSTEPS = (("D", "visual_disc", "acoustic_gen", "visual_D_loss"), ("G", "visual_disc", "acoustic_gen", "acoustic_G_loss"),
+                ("D", "visual_disc", "text_gen", "visual_D_loss"), ("G", "visual_disc", "text_gen", "text_G_loss"),
+                ("D", "text_disc", "acoustic_gen", "text_D_loss"), ("G", "text_disc", "acoustic_gen", "acoustic_G_loss"),
+                ("D", "acoustic_disc", "text_gen", "acoustic_D_loss"), ("G", "acoustic_disc", "text_gen", "text_G_loss"),
+                ("D", "text_disc", "visual_gen", "text_D_loss"), ("G", "text_disc", "visual_gen", "visual_G_loss"),
+                ("D", "acoustic_disc", "visual_gen", "acoustic_D_loss"), ("G", "acoustic_disc", "visual_gen", "visual_G_loss"))
+
     def _batch(self, data: Batch) -> Dict[str, torch.Tensor]:
         n = self.nets
-        real_text, real_visual, real_acoustic = data.text, data.visual, data.acoustic
+        real = {"text_gen": data.text, "visual_gen": data.visual, "acoustic_gen": data.acoustic,
+                "text_disc": data.text, "visual_disc": data.visual, "acoustic_disc": data.acoustic}
+        opts = {"acoustic_gen": self.opt_acoustic_G, "visual_gen": self.opt_visual_G, "text_gen": self.opt_text_G,
+                "acoustic_disc": self.opt_acoustic_D, "visual_disc": self.opt_visual_D, "text_disc": self.opt_text_D}
+        real_text = data.text
         seq_len, batch_size = real_text.size(0), real_text.size(1)
         valid = torch.ones(seq_len, batch_size, 1, device=real_text.device)
         fake = torch.zeros(seq_len, batch_size, 1, device=real_text.device)
@@ -122,20 +138,62 @@ class GANTrainer:
         # all-reduce with a gradient all-reduce); the scale stays a device scalar, so the step is still capturable.
         if self.grad_reducer is not None:
             adv.scale_tensor = self.grad_reducer.local_fraction_tensor(batch_size, real_text.device)
+        disc_step = train_disc_batched if self.batch_disc else train_disc
+
+        def run(kind, d, g):
+            if kind == "D":
+                return disc_step(n[d], real[d], n[g], real[g], opts[d], adv, valid, fake)
+            return train_gen(n[g], real[g], n[d], opts[g], adv, valid, fake)
+
         loss = {}
-        train_disc = train_disc_batched if self.batch_disc else globals()["train_disc"]
-        loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["acoustic_gen"], real_acoustic, self.opt_visual_D, adv, valid, fake)
-        loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["visual_disc"], self.opt_acoustic_G, adv, valid, fake)
-        loss["visual_D_loss"] = train_disc(n["visual_disc"], real_visual, n["text_gen"], real_text, self.opt_visual_D, adv, valid, fake)
-        loss["text_G_loss"] = train_gen(n["text_gen"], real_text, n["visual_disc"], self.opt_text_G, adv, valid, fake)
-        loss["text_D_loss"] = train_disc(n["text_disc"], real_text, n["acoustic_gen"], real_acoustic, self.opt_text_D, adv, valid, fake)
-        loss["acoustic_G_loss"] = train_gen(n["acoustic_gen"], real_acoustic, n["text_disc"], self.opt_acoustic_G, adv, valid, fake)
-        loss["acoustic_D_loss"] = train_disc(n["acoustic_disc"], real_acoustic, n["text_gen"], real_text, self.opt_acoustic_D, adv, valid, fake)
-        loss["text_G_loss"] = train_gen(n["text_gen"], real_text, n["acoustic_disc"], self.opt_text_G, adv, valid, fake)
-        loss["text_D_loss"] = train_disc(n["text_disc"], real_text, n["visual_gen"], real_visual, self.opt_text_D, adv, valid, fake)
-        loss["visual_G_loss"] = train_gen(n["visual_gen"], real_visual, n["text_disc"], self.opt_visual_G, adv, valid, fake)
-        loss["acoustic_D_loss"] = train_disc(n["acoustic_disc"], real_acoustic, n["visual_gen"], real_visual, self.opt_acoustic_D, adv, valid, fake)
-        loss["visual_G_loss"] = train_gen(n["visual_gen"], real_visual, n["acoustic_disc"], self.opt_visual_G, adv, valid, fake)
+        chains = self.chains if (self.overlap and not GF._deterministic["on"]) else 1
+        if chains <= 1:
+            for kind, d, g, key in self.SUBSTEPS:
+                loss[key] = run(kind, d, g)
+            return loss
+
+        # ---- sub-step chains --------------------------------------------------------------------
+        # A sub-step touches exactly two networks (reads / updates their weights, gradient arenas and Adam state), so it
+        # depends only on the previous sub-steps that touched one of the two.  In the reference's order that leaves two
+        # independent runs -- sub-steps 3,4,7,8 use {D_v, G_t, D_a} while 5,6,9,10 use {D_t, G_a, G_v} -- and each
+        # sub-step is one chain of dependent 10-40 us kernels that leaves most SMs idle.  Each sub-step goes to the
+        # chain (stream) whose tail is one of its dependencies, else to another chain, and waits for the events of the
+        # dependencies that live elsewhere: every network still sees exactly the reference's sequence of operations.
+        dev = real_text.device
+        main = torch.cuda.current_stream(dev)
+        pool = self._chain_streams.get(dev.index)
+        if pool is None:
+            pool = [torch.cuda.Stream(device=dev) for _ in range(chains)]
+            for st in pool:
+                GF.register_chain_stream(st)
+            self._chain_streams[dev.index] = pool
+        tail = [None] * len(pool)            # index of the last sub-step enqueued on each chain
+        last = {}                            # network -> (sub-step index, chain, event)
+        used = set()
+        for idx, (kind, d, g, key) in enumerate(self.SUBSTEPS):
+            deps = [last[x] for x in (d, g) if x in last]
+            c = next((dc for (di, dc, _) in sorted(deps, reverse=True) if tail[dc] == di), None)
+            if c is None:
+                c = next((k for k in range(len(pool)) if tail[k] is None), None)
+                if c is None:
+                    c = deps[0][1] if deps else 0
+            st = pool[c]
+            if c not in used:
+                st.wait_stream(main)         # fork: everything already enqueued by the caller (inputs, zeroed arenas)
+                used.add(c)
+            for (_, dc, ev) in deps:
+                if dc != c:
+                    st.wait_event(ev)
+            with torch.cuda.stream(st):
+                loss[key] = run(kind, d, g)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            tail[c] = idx
+            last[d] = last[g] = (idx, c, ev)
+        for c in used:
+            main.wait_stream(pool[c])        # join
+        for t in loss.values():
+            t.record_stream(main)
         return loss
 
 

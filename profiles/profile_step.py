@@ -15,12 +15,13 @@ ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
 ap.add_argument("--stage", default="both", choices=["both", "1", "2"])
 ap.add_argument("--dialogues", type=int, default=32)
 ap.add_argument("--seq-len", type=int, default=94)
+ap.add_argument("--no-batch-disc", action="store_true")
 args = ap.parse_args()
 lib().cdll.ganffn_set_gemm_engine({"auto": 0, "simt": 1, "tc": 2}[args.engine])
 dev = torch.device("cuda:0")
 nets, ffn = train.build_networks(device=dev)
 gan = train.GANTrainer(nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], nets["acoustic_disc"],
-                       nets["visual_disc"], nets["text_disc"])
+                       nets["visual_disc"], nets["text_disc"], batch_disc=not args.no_batch_disc)
 cls = train.ClassifierTrainer(ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev))
 batch = synthetic.make_batch(n_dialogues=args.dialogues, seq_len=args.seq_len).to(dev)
 

@@ -88,7 +88,7 @@ def _compare_updates(name, ours_before, ours_after, port_before, port_after, lr,
 
 
 @pytest.mark.parametrize("batch_disc", [False, True], ids=["two-pass-disc", "batched-disc"])
-@pytest.mark.parametrize("overlap", [False, True], ids=["serial", "lanes"])
+@pytest.mark.parametrize("overlap", [False, True], ids=["serial", "lanes+chains"])
 def test_gan_batch_and_classifier_step_match_reference_port(overlap, batch_disc):
     """batch_disc=False is the reference's train_disc body verbatim (two discriminator passes); True runs them as one
     pass over [real | fake] (train.train_disc_batched) -- both must match the port."""
