@@ -250,7 +250,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     L = lib()
     if args.engine is not None:
-        L.cdll.ganffn_set_gemm_engine({"auto": 0, "simt": 1, "tc": 2}[args.engine])
+        L.cdll.ganffn_set_gemm_engine({"auto": 0, "simt": 1, "tc": 2, "tf32x1": 3}[args.engine])
 
     reducer = parallel.GradReducer() if world > 1 else None
     nets, ffn = train.build_networks(device=dev)
@@ -345,22 +345,60 @@ def run_ours(args):
             os._exit(0)
         return
 
-    # ---- roofline leg: per-GEMM CUDA events over one more step ------------------------------------------------------
-    # every kernel alone on the device for this leg: network lanes and the weight-gradient side stream off, otherwise
-    # an event bracket also measures the time its kernel spends sharing SMs with other streams' kernels
+    # ---- roofline leg: every GEMM of one step bracketed by CUDA events ------------------------------------------------
+    # The step is recorded ONCE MORE as a CUDA graph in serialised form (no lanes, no sub-step chains, weight gradients
+    # on the caller's stream) with the library's GEMM brackets switched on: inside a capture they become external
+    # event-record nodes, so the replay timestamps every GEMM (incl. its split-K fold) with no host launch gap inside
+    # a bracket.  The same replay gives the serialised step time, so the GEMM share is comparable with the ncu launch
+    # list (profiles/), which serialises too.
+    from gan_ffn_b200 import functional as GF
     prev_side = L.cdll.ganffn_set_side_streams(0)
     gan.overlap, cls.overlap = False, False
     torch.cuda.synchronize()
-    L.cdll.ganffn_gemm_profile_enable(1)
-    # keep the device busy for ~80 ms first so that the host runs ahead of it: an event bracket must not contain the
-    # host's launch latency of the kernel it brackets (eager launches are host-bound at ~5 us per kernel)
-    torch.cuda._sleep(int(0.08 * 1.9e9))
-    gan.batch(resident)
-    cls.step(resident, train=True)
-    torch.cuda.synchronize()
-    L.cdll.ganffn_gemm_profile_enable(0)
+    seeds = GF.DeviceSeedStream(dev, base=99)
+    prev_seeds = GF.set_seed_stream(seeds)
+    table_rows, serial_ms, prof_mode = [], None, "graph replay, external event nodes"
+    pg = None
+    try:
+        pg = torch.cuda.CUDAGraph()
+        L.cdll.ganffn_gemm_profile_enable(1)
+        try:
+            with torch.cuda.graph(pg):
+                seeds.advance()
+                gan.batch(resident)
+                cls.step(resident, train=True)
+        finally:
+            L.cdll.ganffn_gemm_profile_enable(0)
+        pg.replay()
+        torch.cuda.synchronize()
+        flush.zero_()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(); pg.replay(); r1.record()
+        torch.cuda.synchronize()
+        serial_ms = r0.elapsed_time(r1)
+    except Exception as exc:       # fall back to eager brackets behind a long device-side sleep
+        prof_mode = f"eager brackets behind a device sleep (graph capture of the brackets failed: {type(exc).__name__}: {exc})"
+        torch.cuda.synchronize()
+        L.cdll.ganffn_gemm_profile_enable(1)
+        torch.cuda._sleep(int(0.08 * 1.9e9))
+        gan.batch(resident)
+        cls.step(resident, train=True)
+        torch.cuda.synchronize()
+        L.cdll.ganffn_gemm_profile_enable(0)
+    GF.set_seed_stream(prev_seeds)
     L.cdll.ganffn_set_side_streams(prev_side)
     gan.overlap, cls.overlap = not args.no_lanes, not args.no_lanes
+    max_rows = 256
+    shp = (ctypes.c_int64 * (6 * max_rows))()
+    tms = (ctypes.c_double * (2 * max_rows))()
+    pg = None                      # the recorded graph holds captured NCCL kernels under DP: drop it before the teardown
+    import gc
+    gc.collect()
+    nrows = int(L.cdll.ganffn_gemm_profile_table(shp, tms, max_rows))
+    for r in range(max(nrows, 0)):
+        M_, N_, K_, ta, bnk, eng = (int(shp[6 * r + j]) for j in range(6))
+        table_rows.append({"M": M_, "N": N_, "K": K_, "transA": ta, "b_is_nk": bnk, "engine": {1: "simt", 2: "tc"}.get(eng, str(eng)),
+                           "launches": int(tms[2 * r + 1]), "ms": tms[2 * r]})
     ms_a, fl_a, n_a = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     L.call("ganffn_gemm_profile_collect", 0, ctypes.byref(ms_a), ctypes.byref(fl_a), ctypes.byref(n_a))
     gemm_ms, gemm_flops, gemm_n = ms_a.value, fl_a.value, n_a.value
@@ -378,14 +416,54 @@ def run_ours(args):
     except Exception:
         pass
     s1, s2 = flops_per_slot(S)
+    for row in table_rows:
+        fl = 2.0 * row["M"] * row["N"] * row["K"] * row["launches"]
+        row["us_per_launch"] = 1e3 * row["ms"] / max(row["launches"], 1)
+        row["tflops"] = fl / (row["ms"] / 1e3) / 1e12 if row["ms"] > 0 else 0.0
+        row["frac_bf16_peak"] = row["tflops"] / peak_tf if peak_tf else None
+        row["frac_3xtf32_ceiling"] = row["tflops"] / (peak_tf / 6.0) if peak_tf else None
+    table_rows.sort(key=lambda r: -r["ms"])
     roofline = {"bound": "tensor", "kernel": "GEMM engine (all linear layers fwd/dgrad/wgrad incl. split-K fold)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "traffic": traffic, "peak_source": peak_src, "launches_per_step": gemm_n,
                 "avg_launch_us": 1e3 * gemm_ms / gemm_n if gemm_n else None,
                 "algorithmic_gflop_per_launch": gemm_flops / gemm_n / 1e9 if gemm_n else None,
-                "gemm_share_of_step": gemm_ms / (ms_total / args.steps) if ms_total else None,
-                "gemm_share_note": "GEMM time is measured with every kernel alone on the device (lanes and side stream off); the timed steps overlap networks, so the share can exceed 1. The weight-gradient products are planned for least SM time, not least latency (they run beside the data-gradient chain), which lowers this per-kernel figure while it shortens the step",
+                "timing": prof_mode, "serialized_step_ms": serial_ms,
+                "gemm_share_of_serialized_step": gemm_ms / serial_ms if serial_ms else None,
+                "gemm_ms_per_step": gemm_ms,
+                "ceiling_3xtf32_tflops": peak_tf / 6.0, "frac_of_3xtf32_ceiling": achieved_tf / (peak_tf / 6.0) if peak_tf else None,
+                "per_shape": table_rows[:40],
+                "gemm_share_note": "GEMM time and the serialised step time come from the same replay (no lanes, no chains, weight gradients on the caller's stream); the timed headline steps overlap networks and sub-steps, so they are shorter than the serialised step",
                 "note": "fp32-parity arithmetic: FFMA tiles or 3xTF32 tcgen05 (3 MMAs per product at half the bf16 rate), so frac <= ~0.17 by construction against the bf16 peak"}
+
+    # ---- reduced-precision variant (north_star: rtol 2e-2 if offered): the same step with one TF32 MMA per product ----
+    reduced = None
+    if args.engine is None and not args.no_reduced:
+        try:
+            prev_engine = L.cdll.ganffn_set_gemm_engine(3)
+            st2 = train.GraphedTrainStep(gan, cls, seed=4242 + rank, enabled=not args.eager)
+            for _ in range(3):
+                st2(resident)
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            for a, b_ in evs:
+                flush.zero_()
+                a.record(); st2(resident); b_.record()
+            barrier()
+            ms_r = sum(a.elapsed_time(b_) for a, b_ in evs) / len(evs)
+            t = torch.tensor([ms_r], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_r = float(t.item())
+            reduced = {"engine": "tf32x1", "dtype": "tf32 operands (10-bit mantissa), fp32 accumulate, one tcgen05 MMA per product",
+                       "ms_per_step": ms_r, "value": slots / (ms_r / 1e3), "unit": UNIT, "steps": len(evs),
+                       "tolerance": "rtol 2e-2 (tests/test_gpu_nets.py::test_reduced_precision_variant)",
+                       "note": "separate line, never the fp32-parity headline"}
+            st2.release()
+        except Exception as exc:
+            reduced = {"error": f"{type(exc).__name__}: {exc}"}
+        finally:
+            L.cdll.ganffn_set_gemm_engine(prev_engine)
 
     # ---- the HBM-bound kernel of the path: fused Adam over the largest arena (28 B/param), timed alone ------------------
     hbm = None
@@ -435,7 +513,7 @@ def run_ours(args):
                 eager = {"error": f"{type(exc).__name__}: {exc}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32" if args.engine != "tf32x1" else "tf32x1 (reduced-precision variant, not the parity path)", "data": "synthetic",
                 "config": {"workload": WORKLOAD if (S, B) == (S_IEMOCAP, B_IEMOCAP) else f"train_step S={S} B={B} per GPU",
                            "seq_len": S, "dialogues_per_gpu": B, "global_dialogues": B * world, "parallelism": f"dp{world} by dialogue",
                            "stage1_ms": stage1_ms, "stage2_ms": stage2_ms,
@@ -454,6 +532,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if eager is not None:
             line["gpu_eager_baseline"] = eager
+        if reduced is not None:
+            line["reduced_precision"] = reduced
         if hbm is not None:
             line["roofline_hbm"] = hbm
         if graph is not None:
@@ -478,8 +558,10 @@ def main():
     ap.add_argument("--seq-len", type=int, default=S_IEMOCAP)
     ap.add_argument("--dialogues", type=int, default=B_IEMOCAP, help="dialogues per GPU")
     ap.add_argument("--ref-dialogues", type=int, default=0, help="dialogues per step of the CPU reference arm (0 = the same as --dialogues)")
-    ap.add_argument("--engine", default=None, choices=["auto", "simt", "tc"])
+    ap.add_argument("--engine", default=None, choices=["auto", "simt", "tc", "tf32x1"],
+                    help="GEMM engine; tf32x1 = the reduced-precision variant (one TF32 MMA per product, rtol 2e-2), never the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-precision (tf32x1) leg")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-torch-eager-on-GPU comparator leg")
     ap.add_argument("--no-graph", action="store_true", help="skip the dialogue-graph kernel leg (HBM GB/s of edge build / gathers)")
     ap.add_argument("--graph-utterances", type=int, default=1_000_000)

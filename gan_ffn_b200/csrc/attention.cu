@@ -8,7 +8,8 @@
 // operand read is either warp-uniform (broadcast of a K/V/Q/dO row) or walks consecutive floats of an odd-stride
 // S x S row: one wavefront per instruction.  (A first version with one thread per query and no groups had 3 warps
 // per CTA and ran latency-bound: 26/100 us fwd/bwd per d=100 layer at S=94, B=32.)
-#include "common.cuh"
+#include <stdlib.h>
+#include "kernels.h"
 
 namespace ganffn {
 namespace {
@@ -653,12 +654,28 @@ int launch_bwd(const float* qkv, const float* o, const float* lse, const float* 
 
 }  // namespace
 
+// bit 0: forward on the tensor-core kernels (attention_mma.cu), bit 1: backward.  GANFFN_ATTN=0 selects the FFMA
+// kernels of this file (kept as the exact-fp32 cross-check and for A/B runs), 1 / 2 one direction only.
+// Default (measured, warm L2, S=94 B=32, tools/attn_time.py): head_dim 64 -- tensor-core kernels 28-30 us forward /
+// 84-95 us backward against 40-42 / 97-98 us for the FFMA kernels; head_dim 10 -- both are bound by the latency of one
+// warp's dependent chain (16-20 / 39-50 us on mma.sync, 16-17 / 29-33 us on FFMA with four warps per 32 rows), so the
+// narrow heads stay on the FFMA kernels.
+static int attn_engine(int head_dim) {
+  static const int mode = getenv("GANFFN_ATTN") ? atoi(getenv("GANFFN_ATTN")) : -1;
+  if (mode >= 0) return mode;
+  return head_dim >= 32 ? 3 : 0;
+}
+
 int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed,
                   int site, cudaStream_t st) {
   GANFFN_CHECK_ARG(S >= 1 && S <= GANFFN_MAX_SEQ, "attention: seq_len %d outside [1,%d] (model.py:1179)", S,
                    GANFFN_MAX_SEQ);
   GANFFN_CHECK_ARG(B >= 1 && nhead >= 1 && d % nhead == 0, "attention: d=%d not divisible by nhead=%d", d, nhead);
   GANFFN_CHECK_ARG(p >= 0.f && p < 1.f, "attention: dropout p=%f", p);
+  if (attn_engine(d / nhead) & 1) {
+    const int rc = attention_fwd_mma(qkv, o, lse, S, B, d, nhead, p, seed, site, st);
+    if (rc >= 0) return rc;
+  }
   switch (d / nhead) {
     case 8: return launch_fwd<8>(qkv, o, lse, S, B, d, nhead, p, seed, site, st);
     case 10: return launch_fwd<10>(qkv, o, lse, S, B, d, nhead, p, seed, site, st);
@@ -675,6 +692,10 @@ int attention_bwd(const float* qkv, const float* o, const float* lse, const floa
   GANFFN_CHECK_ARG(S >= 1 && S <= GANFFN_MAX_SEQ, "attention: seq_len %d outside [1,%d] (model.py:1179)", S,
                    GANFFN_MAX_SEQ);
   GANFFN_CHECK_ARG(B >= 1 && nhead >= 1 && d % nhead == 0, "attention: d=%d not divisible by nhead=%d", d, nhead);
+  if (attn_engine(d / nhead) & 2) {
+    const int rc = attention_bwd_mma(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed, site, st);
+    if (rc >= 0) return rc;
+  }
   switch (d / nhead) {
     case 8: return launch_bwd<8>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed, site, st);
     case 10: return launch_bwd<10>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed, site, st);

@@ -33,10 +33,19 @@ static bool use_tc(bool transA, bool b_is_nk, int lda, int ldb, int ldc, int M, 
 // ---- per-GEMM CUDA-event profiling (bench.py roofline leg) ------------------------------------------------
 // When enabled, every GEMM (including its split-K fold) is bracketed by two events on the launching
 // stream; ganffn_gemm_profile_collect() synchronises and sums elapsed time and algorithmic FLOPs per engine.
-struct ProfEntry { cudaEvent_t a, b; double flops; int engine; };
+struct ProfEntry { cudaEvent_t a, b; double flops; int engine; int M, N, K, transA, b_is_nk; };
 static bool g_prof = false;
 static std::vector<ProfEntry> g_prof_entries;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+
+// Inside a stream capture the brackets become *external* event-record nodes: the replayed graph then timestamps every
+// GEMM without any host launch gap between the two records (bench.py times its roofline leg this way).
+static void prof_record(cudaEvent_t ev, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+  else cudaEventRecord(ev, st);
+}
 
 static ProfEntry prof_begin(double flops, int engine, cudaStream_t st) {
   ProfEntry e;
@@ -47,7 +56,7 @@ static ProfEntry prof_begin(double flops, int engine, cudaStream_t st) {
     cudaEventCreate(&e.a); cudaEventCreate(&e.b);
   }
   e.flops = flops; e.engine = engine;
-  cudaEventRecord(e.a, st);
+  prof_record(e.a, st);
   return e;
 }
 
@@ -55,7 +64,10 @@ int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_i
          int K, const Epilogue& ep, float* scratch, int64_t scratch_floats, cudaStream_t st) {
   const bool tc = use_tc(transA, b_is_nk, lda, ldb, ldc, M, N, K, A, B);
   ProfEntry pe{};
-  if (g_prof) pe = prof_begin(2.0 * M * N * K, tc ? GANFFN_GEMM_TC : GANFFN_GEMM_SIMT, st);
+  if (g_prof) {
+    pe = prof_begin(2.0 * M * N * K, tc ? GANFFN_GEMM_TC : GANFFN_GEMM_SIMT, st);
+    pe.M = M; pe.N = N; pe.K = K; pe.transA = transA; pe.b_is_nk = b_is_nk;
+  }
   int rc;
   if (tc) {
     rc = gemm_tc(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, ep, scratch, scratch_floats, st);
@@ -65,7 +77,7 @@ int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_i
     rc = gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, e2, scratch, scratch_floats, st);
   }
   if (g_prof) {
-    cudaEventRecord(pe.b, st);
+    prof_record(pe.b, st);
     g_prof_entries.push_back(pe);
   }
   return rc;
@@ -135,9 +147,32 @@ int ganffn_gemm_profile_collect(int engine, double* total_ms, double* total_flop
   *total_ms = ms; *total_flops = fl; *launches = n;
   return GANFFN_OK;
 }
+int64_t ganffn_gemm_profile_table(int64_t* shapes, double* ms, int64_t max_rows) {
+  if (!shapes || !ms || max_rows <= 0) { set_error("gemm_profile_table: null pointer"); return -1; }
+  int64_t rows = 0;
+  for (auto& e : g_prof_entries) {
+    if (cudaEventSynchronize(e.b) != cudaSuccess) { set_error("gemm_profile_table: event sync failed"); return -1; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) { set_error("gemm_profile_table: elapsed time failed"); return -1; }
+    int64_t r = 0;
+    for (; r < rows; ++r)
+      if (shapes[6 * r] == e.M && shapes[6 * r + 1] == e.N && shapes[6 * r + 2] == e.K && shapes[6 * r + 3] == e.transA &&
+          shapes[6 * r + 4] == e.b_is_nk && shapes[6 * r + 5] == e.engine)
+        break;
+    if (r == rows) {
+      if (rows == max_rows) continue;
+      shapes[6 * r] = e.M; shapes[6 * r + 1] = e.N; shapes[6 * r + 2] = e.K; shapes[6 * r + 3] = e.transA;
+      shapes[6 * r + 4] = e.b_is_nk; shapes[6 * r + 5] = e.engine;
+      ms[2 * r] = 0.0; ms[2 * r + 1] = 0.0;
+      ++rows;
+    }
+    ms[2 * r] += t; ms[2 * r + 1] += 1.0;
+  }
+  return rows;
+}
 int ganffn_set_gemm_engine(int engine) {
   int prev = g_gemm_engine;
-  if (engine >= GANFFN_GEMM_AUTO && engine <= GANFFN_GEMM_TC) g_gemm_engine = engine;
+  if (engine >= GANFFN_GEMM_AUTO && engine <= GANFFN_GEMM_TF32X1) g_gemm_engine = engine;
   return prev;
 }
 

@@ -67,6 +67,7 @@ struct TcParams {
   int k_per_split;   // multiple of BK
   float* partial; int Np;
   int out_mode;      // 0 fused epilogue, 1 split-K partials, 2 red.global.add (vector), 3 red.global.add (scalar)
+  int x1;            // reduced-precision variant (GANFFN_GEMM_TF32X1): hi parts only, one MMA per product
   Epilogue ep;
 };
 
@@ -227,7 +228,7 @@ __device__ __forceinline__ void load_a(float (&v)[16], const float* __restrict__
 // tf32 operand, i.e. truncates lo (|lo| <= 2^-11 |x|, so the truncation is <= 2^-21 |x|).
 // taddr: the warp's lane quadrant, first column of its k-half (hi); lo lives 32 columns further.
 template <bool KMAJ>
-__device__ __forceinline__ void store_a(const float (&v)[16], uint32_t taddr) {
+__device__ __forceinline__ void store_a(const float (&v)[16], uint32_t taddr, int x1 = 0) {
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -237,11 +238,13 @@ __device__ __forceinline__ void store_a(const float (&v)[16], uint32_t taddr) {
   if (KMAJ) {
     tmem_st_16x256b_x2(taddr, h);
     tmem_st_16x256b_x2(taddr + (16u << 16), h + 8);
-    tmem_st_16x256b_x2(taddr + 32, l);
-    tmem_st_16x256b_x2(taddr + (16u << 16) + 32, l + 8);
+    if (!x1) {
+      tmem_st_16x256b_x2(taddr + 32, l);
+      tmem_st_16x256b_x2(taddr + (16u << 16) + 32, l + 8);
+    }
   } else {
     tmem_st16(taddr, h);
-    tmem_st16(taddr + 32, l);
+    if (!x1) tmem_st16(taddr + 32, l);
   }
   tmem_st_wait();
 }
@@ -264,7 +267,7 @@ __device__ __forceinline__ void load_b(float4 (&v)[BCH], const float* __restrict
   }
 }
 
-__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uint32_t lo) {
+__device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uint32_t lo, int x1 = 0) {
 #pragma unroll
   for (int i = 0; i < BCH; ++i) {
     const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -275,7 +278,7 @@ __device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uin
       l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));   // truncated by the tensor core (see store_a)
     }
     sts128(hi + i * 4096, h[0], h[1], h[2], h[3]);
-    sts128(lo + i * 4096, l[0], l[1], l[2], l[3]);
+    if (!x1) sts128(lo + i * 4096, l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -554,7 +557,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
 #pragma unroll
             for (int j = 0; j < 16; ++j) rowsum += buf[r][j];
           }
-          store_a<!TA>(buf[r], trow + (uint32_t)(s * 64));
+          store_a<!TA>(buf[r], trow + (uint32_t)(s * 64), p.x1);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full + s));
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
           const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
           mbar_wait(smem_u32(empty + s), ph ^ 1u);
           const uint32_t st = b_smem + (uint32_t)(s * STAGE);
-          store_b(buf[r], st, st + B_TILE);
+          store_b(buf[r], st, st + B_TILE, p.x1);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full + s));
@@ -641,8 +644,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
             const uint64_t dbh = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP);
             const uint64_t dbl = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP + (B_TILE >> 4));
             const uint32_t acc = (j > 0 || kb > 0) ? 1u : 0u;
-            umma_tf32_ts(d_corr, a_hi + 32 + 8 * j, dbh, idesc, acc);
-            umma_tf32_ts(d_corr, a_hi + 8 * j, dbl, idesc, 1u);
+            if (!p.x1) {
+              umma_tf32_ts(d_corr, a_hi + 32 + 8 * j, dbh, idesc, acc);
+              umma_tf32_ts(d_corr, a_hi + 8 * j, dbl, idesc, 1u);
+            }
             umma_tf32_ts(d_main, a_hi + 8 * j, dbh, idesc, acc);
           }
         }
@@ -666,7 +671,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
       uint32_t r[32], rl[32];
       const uint32_t tr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
       tmem_ld32(tr + TM_MAIN, r);
-      tmem_ld32(tr + TM_CORR, rl);
+      if (!p.x1) {
+        tmem_ld32(tr + TM_CORR, rl);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) rl[q] = 0u;
+      }
       tmem_ld_wait();
       if (t == 0) TR(70);
 #pragma unroll
@@ -773,7 +783,7 @@ __global__ void __launch_bounds__(A_NTHREADS, 1) gemm_tc_astat_kernel(const TcPa
         if (kb < nkb) load_a<true>(buf[kb], ap + kb * BK, p.lda, a_rows_left, p.K - (a_k0 + kb * BK));
 #pragma unroll
       for (int kb = 0; kb < AKB; ++kb)
-        if (kb < nkb) store_a<true>(buf[kb], trow + (uint32_t)(kb * 64));
+        if (kb < nkb) store_a<true>(buf[kb], trow + (uint32_t)(kb * 64), p.x1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(a_full));
@@ -795,7 +805,12 @@ __global__ void __launch_bounds__(A_NTHREADS, 1) gemm_tc_astat_kernel(const TcPa
       if (live) {
         const uint32_t tr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 2 * ABN + col0);
         tmem_ld32(tr, r);
-        tmem_ld32(tr + ABN, rl);
+        if (!p.x1) {
+          tmem_ld32(tr + ABN, rl);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) rl[q] = 0u;
+        }
         tmem_ld_wait();
       }
       tc_fence_before();
@@ -867,7 +882,7 @@ __global__ void __launch_bounds__(A_NTHREADS, 1) gemm_tc_astat_kernel(const TcPa
               l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));
             }
             sts128(hi + i * 2048, h[0], h[1], h[2], h[3]);
-            sts128(hi + AB_TILE + i * 2048, l[0], l[1], l[2], l[3]);
+            if (!p.x1) sts128(hi + AB_TILE + i * 2048, l[0], l[1], l[2], l[3]);
           }
         }
       }
@@ -908,8 +923,10 @@ __global__ void __launch_bounds__(A_NTHREADS, 1) gemm_tc_astat_kernel(const TcPa
               const uint64_t dbh = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP);
               const uint64_t dbl = ((uint64_t)bdesc_hi32 << 32) | (uint64_t)(b_lo32 + j * B_JSTEP + (AB_TILE >> 4));
               const uint32_t acc = (j > 0 || kb > 0) ? 1u : 0u;
-              umma_tf32_ts(d_corr, a_hi + 32 + 8 * j, dbh, idesc, acc);
-              umma_tf32_ts(d_corr, a_hi + 8 * j, dbl, idesc, 1u);
+              if (!p.x1) {
+                umma_tf32_ts(d_corr, a_hi + 32 + 8 * j, dbh, idesc, acc);
+                umma_tf32_ts(d_corr, a_hi + 8 * j, dbl, idesc, 1u);
+              }
               umma_tf32_ts(d_main, a_hi + 8 * j, dbh, idesc, acc);
             }
           }
@@ -991,8 +1008,13 @@ TcPlan tc_plan(int M, int N, int K) {
     if (kps > 1024 && nkb / (sp + 1) >= 4) continue;
     const int splits = cdiv(K, kps);
     const int waves = cdiv((int64_t)tiles * splits, 148);
-    double cost = waves * (cdiv(kps, BK) * 800.0 + 3500.0);
+    const double per_cta = cdiv(kps, BK) * 800.0 + 3500.0;
+    double cost = waves * per_cta;
     if (splits > 1) cost += 4000.0 + (double)M * N * (splits + 1) * 4.0 / 4000.0;   // fold kernel (~4 KB/cycle)
+    // With concurrent sub-step chains the step is bound by SM-slot time as much as by latency (one CTA of this
+    // kernel owns its SM): weigh the slots a plan occupies (tuning knob, r2 A/B runs).
+    static const double slot_w = getenv("GANFFN_SLOT_WEIGHT") ? atof(getenv("GANFFN_SLOT_WEIGHT")) : 0.0;
+    cost += slot_w * per_cta * (double)tiles * splits / 148.0;
     if (cost < best_cost) { best_cost = cost; best = TcPlan{splits, kps}; }
   }
   return best;
@@ -1077,6 +1099,7 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     TcParams p;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.k_per_split = pa.kps; p.partial = nullptr; p.Np = Np; p.ep = ep;
+    p.x1 = g_gemm_engine == GANFFN_GEMM_TF32X1;
     p.out_mode = ((N & 3) == 0 && (ldc & 3) == 0 && al16(C)) ? 2 : 3;
     return launch_tc(p, transA, b_is_nk, EPI_PLAIN, dim3(cdiv(N, BN), cdiv(M, BM), pa.splits), st);
   }
@@ -1084,9 +1107,11 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     TcParams p;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.k_per_split = (int)round_up(K, BK); p.partial = nullptr; p.Np = Np; p.ep = ep;
+    p.x1 = g_gemm_engine == GANFFN_GEMM_TF32X1;
     p.out_mode = 0;
     const int mtiles = cdiv(M, BM), ntiles = cdiv(N, ABN);
-    const int groups = std::max(1, std::min(ntiles, 148 / std::max(1, mtiles)));
+    static const int astat_div = getenv("GANFFN_ASTAT_DIV") ? atoi(getenv("GANFFN_ASTAT_DIV")) : 1;   // tuning knob
+    const int groups = std::max(1, std::min(ntiles, 148 / std::max(1, mtiles)) / std::max(1, astat_div));
     const int epi = pick_epilogue(ep, C, ldc, N);
     return b_is_nk ? launch_astat2<true>(p, epi, dim3(groups, mtiles, 1), st)
                    : launch_astat2<false>(p, epi, dim3(groups, mtiles, 1), st);
@@ -1099,6 +1124,7 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
   TcParams p;
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.M = M; p.N = N; p.K = K; p.k_per_split = pl.kps; p.partial = scratch; p.Np = Np; p.ep = ep;
+  p.x1 = g_gemm_engine == GANFFN_GEMM_TF32X1;
   p.out_mode = pl.splits > 1 ? 1 : 0;
   dim3 grid(cdiv(N, BN), cdiv(M, BM), pl.splits);
   const int epi = pl.splits > 1 ? EPI_PLAIN : pick_epilogue(ep, C, ldc, N);

@@ -22,6 +22,12 @@ int attention_fwd(const float* qkv, float* o, float* lse, int S, int B, int d, i
 int attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
                   int nhead, float p, Seed seed, int site, cudaStream_t st);
 
+// attention_mma.cu (tensor-core path, 3xTF32 on mma.sync fragments); return -1 for an unsupported head_dim
+int attention_fwd_mma(const float* qkv, float* o, float* lse, int S, int B, int d, int nhead, float p, Seed seed,
+                      int site, cudaStream_t st);
+int attention_bwd_mma(const float* qkv, const float* o, const float* lse, const float* d_o, float* dqkv, int S, int B, int d,
+                      int nhead, float p, Seed seed, int site, cudaStream_t st);
+
 // rowwise.cu
 int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, int T, int d, cudaStream_t st);
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,

@@ -53,6 +53,10 @@ extern "C" {
 #define GANFFN_GEMM_AUTO 0
 #define GANFFN_GEMM_SIMT 1   /* fp32 FFMA tiles */
 #define GANFFN_GEMM_TC 2     /* tcgen05 kind::tf32, 3xTF32 error-compensated */
+#define GANFFN_GEMM_TF32X1 3 /* REDUCED PRECISION variant: one tcgen05 kind::tf32 MMA per product (10-bit mantissa operands,
+                              * fp32 accumulate) -- the reduced-precision variant north_star allows at rtol 2e-2 (it names
+                              * bf16; single-pass TF32 keeps 3 more mantissa bits at the same one-MMA-per-product cost model).
+                              * Never the fp32-parity headline: bench.py reports it as a separate line. */
 
 /* ---- library state -------------------------------------------------------------------- */
 int ganffn_version(void);
@@ -81,6 +85,11 @@ int ganffn_set_side_streams(int on);
  * (GANFFN_GEMM_AUTO = all) since the last collect, and clears the record. */
 void ganffn_gemm_profile_enable(int on);
 int ganffn_gemm_profile_collect(int engine, double* total_ms, double* total_flops, int64_t* launches);
+/* Per-shape view of the same record (call before collect(), which clears it): row r is
+ * shapes[6r..6r+5] = {M, N, K, transA, b_is_nk, engine}, ms[2r] = summed milliseconds, ms[2r+1] = launches.
+ * Returns the number of rows (<= max_rows), -1 on error.  When the bracketed calls were recorded inside a stream
+ * capture the brackets are external event-record nodes: replay the graph, then read the table. */
+int64_t ganffn_gemm_profile_table(int64_t* shapes, double* ms, int64_t max_rows);
 
 /* ---- primitives (each is also used by the whole-network calls) ------------------------ */
 

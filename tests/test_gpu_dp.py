@@ -134,3 +134,68 @@ def test_dp_trainer_graph_replay_equals_single_gpu_trainer(tmp_path):
         assert p.exitcode == 0, f"worker exit code {p.exitcode}"
     ok = torch.load(out)
     assert all(ok.values()), ok
+
+
+def _full_trainers_worker(rank, world, port, out_path):
+    """The real trainers (GANTrainer with its six FusedAdam optimizers + ClassifierTrainer) under a GradReducer,
+    with UNEVEN shards and a batch size that changes from one batch to the next (5 dialogues -> 3+2, then 3 -> 2+1),
+    against the single-GPU trainers on the whole global batches.  Dropout off (modules pinned in eval mode)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from gan_ffn_b200 import parallel, synthetic, train
+    parallel.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    red = parallel.GradReducer()
+    w = torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev)
+    batches = [synthetic.make_batch(n_dialogues=5, lengths=[30, 17, 22, 8, 25], seed=9),
+               synthetic.make_batch(n_dialogues=3, lengths=[12, 30, 21], seed=10)]
+    keys = ["acoustic_D_loss", "acoustic_G_loss", "text_D_loss", "text_G_loss", "visual_D_loss", "visual_G_loss"]
+
+    def run(reducer):
+        nets, ffn = train.build_networks(device=dev)
+        for m in list(nets.values()) + [ffn]:
+            m.eval()
+            m.train = (lambda mod: (lambda mode=True: mod))(m)
+        gan = train.GANTrainer(nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], nets["acoustic_disc"],
+                               nets["visual_disc"], nets["text_disc"], grad_reducer=reducer, world_size=world)
+        cls = train.ClassifierTrainer(ffn, w, grad_reducer=reducer)
+        out = []
+        for gb in batches:
+            b = (parallel.shard_batch(gb, world, rank) if reducer is not None else gb).to(dev)
+            losses = gan.batch(b)
+            vals = torch.stack([losses[k] for k in keys])
+            if reducer is not None:
+                dist.all_reduce(vals)           # BCE: every rank holds local_mean * B_local / B_global
+            l2, _, _ = cls.step(b, train=True)  # already the global loss on every rank
+            out.append(torch.cat([vals, l2.reshape(1)]))
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().reshape(-1) for m in nets.values() for p in m.parameters()])
+        return torch.stack(out), flat
+
+    l_dp, w_dp = run(red)
+    l_one, w_one = run(None)
+    ok = {"losses_batch0": bool(torch.allclose(l_dp[0], l_one[0], rtol=1e-4, atol=0)),
+          "losses_batch1": bool(torch.allclose(l_dp[1], l_one[1], rtol=5e-4, atol=0)),
+          "weights_mean": float((w_dp - w_one).abs().mean()) < 0.02 * 5e-5,
+          "rel_loss_err": float(((l_dp - l_one).abs() / l_one.abs()).max())}
+    if rank == 0:
+        torch.save(ok, out_path)
+    if not parallel.shutdown():
+        os._exit(3)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_dp_real_trainers_with_uneven_changing_shards_equal_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ok.pt")
+    ctx = mp.spawn(_full_trainers_worker, args=(2, _free_port(), out), nprocs=2, join=False)
+    for p in ctx.processes:
+        p.join(timeout=600)
+        assert p.exitcode == 0, f"worker exit code {p.exitcode}"
+    ok = torch.load(out)
+    print("PARITY dp-trainers", ok)
+    assert all(v for k, v in ok.items() if k != "rel_loss_err"), ok
