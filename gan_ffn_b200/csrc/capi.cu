@@ -319,6 +319,10 @@ int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const floa
                  dx, scratch, train, p_head, Seed(seed, seed_dev), accumulate, S(stream));
 }
 
+int ganffn_net_bwd_layer_wait(void* bwd_stream, int layer, void* waiting_stream) {
+  return net_bwd_layer_wait(S(bwd_stream), layer, S(waiting_stream));
+}
+
 int64_t ganffn_net_stash_floats(int kind, int S_, int B, int d_in, int d, int nhead, int dff, int nlayers, int h1,
                                 int h2) {
   NetDims nd = dims(kind, S_, B, d_in, d, nhead, dff, nlayers, h1, h2);

@@ -73,6 +73,7 @@ int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const fl
 int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const float* x, const float* out,
             const float* d_out, const float* stash, float* grads, float* dx, float* scratch, int train, float p_head,
             Seed seed, int accumulate, cudaStream_t st);
+int net_bwd_layer_wait(cudaStream_t bwd_stream, int layer, cudaStream_t waiting);
 int64_t net_stash_floats(const NetDims& nd);
 int64_t net_scratch_floats(const NetDims& nd);
 int net_check(const NetDims& nd);

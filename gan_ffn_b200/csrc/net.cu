@@ -119,10 +119,16 @@ struct Ctx {
 // optimizer runs.  They are issued on a second stream that forks from / joins the caller's stream with events (legal
 // inside CUDA-graph capture), so they fill SMs the 24..144-CTA data-gradient kernels leave idle.  One side stream
 // per caller stream (networks on different lanes each get their own); created on first use, never destroyed.
+constexpr int MAX_LAYER_EVENTS = 32;
 struct SideCtx {
   cudaStream_t side = nullptr;
   cudaEvent_t ready[4], done[4], join;   // slots: L2, L1, OUT, IN
   bool pending[4] = {false, false, false, false};
+  // layer_done[l]: every gradient of encoder layer l (weight gradients on the side stream AND the LayerNorm / bias
+  // gradients the data-gradient stream wrote) has landed -- what a per-layer gradient all-reduce waits for
+  // (ganffn_net_bwd_layer_wait; parallel.py overlaps the all-reduce of layer l with the backward of layers l-1 .. 0)
+  cudaEvent_t layer_done[MAX_LAYER_EVENTS], layer_tmp;
+  int layers_recorded = 0;
 };
 enum { W_L2 = 0, W_L1 = 1, W_OUT = 2, W_IN = 3 };
 
@@ -144,11 +150,30 @@ SideCtx* side_ctx(cudaStream_t st) {
     cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->layer_tmp, cudaEventDisableTiming);
+  for (int i = 0; i < MAX_LAYER_EVENTS; ++i) cudaEventCreateWithFlags(&c->layer_done[i], cudaEventDisableTiming);
   table[st] = c;
   return c;
 }
 
 }  // namespace
+
+// `waiting` waits (device-side) until every gradient of encoder layer `layer` of the LAST ganffn_net_bwd issued on
+// `bwd_stream` has landed.  GANFFN_ERR_ARG when that call recorded no per-layer events (side streams off, or created
+// during a stream capture): the caller then waits for the whole backward pass instead.
+int net_bwd_layer_wait(cudaStream_t bwd_stream, int layer, cudaStream_t waiting) {
+  if (!g_side_streams) { set_error("net_bwd_layer_wait: side streams are off"); return GANFFN_ERR_ARG; }
+  SideCtx* sx = side_ctx(bwd_stream);
+  if (sx == nullptr || layer < 0 || layer >= sx->layers_recorded) {
+    set_error("net_bwd_layer_wait: no per-layer event for layer %d on this stream", layer);
+    return GANFFN_ERR_ARG;
+  }
+  if (cudaStreamWaitEvent(waiting, sx->layer_done[layer], 0) != cudaSuccess) {
+    set_error("net_bwd_layer_wait: cudaStreamWaitEvent failed");
+    return GANFFN_ERR_CUDA;
+  }
+  return GANFFN_OK;
+}
 
 int net_check(const NetDims& nd) {
   GANFFN_CHECK_ARG(nd.kind == GANFFN_NET_GENERATOR || nd.kind == GANFFN_NET_DISCRIMINATOR, "net: kind %d", nd.kind);
@@ -359,7 +384,13 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
       Epilogue ep; ep.residual = dz1; ep.ldr = d;
       GANFFN_TRY(cx.dgrad(scratch + sc.dqkv, P(lo[IN_W]), da, T, 3 * d, d, ep));
     }
+    if (sx && l < MAX_LAYER_EVENTS) {   // layer l's gradients are complete once both streams get here
+      cudaEventRecord(sx->layer_tmp, st);
+      cudaStreamWaitEvent(sx->side, sx->layer_tmp, 0);
+      cudaEventRecord(sx->layer_done[l], sx->side);
+    }
   }
+  if (sx) sx->layers_recorded = nd.L < MAX_LAYER_EVENTS ? nd.L : MAX_LAYER_EVENTS;
   if (sx) {   // join: every weight gradient has landed before the caller's stream continues
     cudaEventRecord(sx->join, sx->side);
     cudaStreamWaitEvent(st, sx->join, 0);

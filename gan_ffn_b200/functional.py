@@ -287,6 +287,10 @@ class ParamArena:
         self.requires_grad = any(p.requires_grad for p in params)
         self.prezeroed = False      # FusedAdam.zero_grad() already cleared ``grad`` on the caller's stream
         self.zero_event, self.zero_stream = None, None
+        # data parallelism: FusedAdam.zero_grad() arms ``reduce_hook`` = {"reducer", "expected", "seen"}; the backward pass
+        # that completes the expected count launches the per-layer all-reduces (overlapped with the rest of that
+        # pass) and leaves their handles in ``reduce_works`` for FusedAdam.step() to wait on
+        self.reduce_hook, self.reduce_works = None, None
 
     def prezero(self) -> None:
         """zero_grad(set_to_none=True) for an arena: the ``.grad`` views are dropped by the caller; the buffer is
@@ -375,6 +379,12 @@ class _NetFunction(torch.autograd.Function):
                ptr(ctx.stash), ptr(arena.grad), ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
                spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, ctx.seed_ptr, 1, _stream(x))
         ctx.stash = None
+        hook = arena.reduce_hook
+        if hook is not None:
+            hook["seen"] += 1
+            if hook["seen"] == hook["expected"]:
+                arena.reduce_works = hook["reducer"].reduce_arena_by_layer(arena, spec.nlayers, cur)
+                arena.reduce_hook = None
         return dx, None, None, None, None, None, None, None, None
 
 
@@ -465,6 +475,12 @@ class _ArenaLinearFunction(torch.autograd.Function):
             wsd = scratch(x.device, nsd, _scratch_tag(x.device) + "/lin")
             _call(x, "ganffn_linear_dgrad", ptr(dy), arena.flat.data_ptr() + 4 * ctx.ow, None, ptr(dx), M, ctx.n_out, K,
                   ptr(wsd), nsd, _stream(x))
+        hook = arena.reduce_hook
+        if hook is not None:       # this pass counts as one of the expected passes into the arena (see _NetFunction.backward)
+            hook["seen"] += 1
+            if hook["seen"] == hook["expected"]:
+                arena.reduce_works = hook["reducer"].reduce_arena_whole(arena, cur)
+                arena.reduce_hook = None
         return dx, None, None, None, None, None
 
 

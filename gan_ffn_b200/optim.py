@@ -34,6 +34,14 @@ class FusedAdam:
         self.modules: List[torch.nn.Module] = list(modules)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.grad_reducer = grad_reducer          # parallel.GradReducer or None
+        # overlap the gradient all-reduce with the backward pass (per-layer buckets); ``expected_backwards`` = how many
+        # backward passes add into a network's arena before step() (1, or 2 for the reference's two-pass train_disc)
+        self.overlap_reduce = True
+        self.expected_backwards = 1
+        # several passes into one arena may only be overlapped when they are ordered behind each other (the network pass
+        # and the `object` projection of the batched visual discriminator are); concurrent passes on different lanes
+        # (the two-pass train_disc body) fall back to one all-reduce per arena at step()
+        self.sequential_backwards = False
         self.grad_scale = 1.0
         self.state = {}                           # id(arena or param) -> dict(step, m, v)
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
@@ -71,6 +79,12 @@ class FusedAdam:
         if set_to_none:
             for ar in self._arenas():
                 ar.prezero()   # one memset now, on the caller's stream, instead of one inside the first backward
+                ar.reduce_works = None
+                # data parallel: the backward pass that completes the expected number of passes into this arena launches
+                # the all-reduce itself, layer by layer (functional._NetFunction.backward -> GradReducer.reduce_arena_by_layer)
+                ar.reduce_hook = ({"reducer": self.grad_reducer, "expected": int(self.expected_backwards), "seen": 0}
+                                  if (self.grad_reducer is not None and self.overlap_reduce and ar.grad.is_cuda and
+                                      (self.expected_backwards == 1 or self.sequential_backwards)) else None)
 
     def _state_for(self, key, like: torch.Tensor):
         """Adam state of an arena / loose parameter.  The step count lives on the device (``step_t``) and is bumped by
@@ -95,7 +109,17 @@ class FusedAdam:
         live = [ar for ar in arenas if ar.grads_live()]
         loose = [p for p in self._loose(arenas) if p.grad is not None]
         if self.grad_reducer is not None:
-            self.grad_reducer.reduce([ar.grad for ar in live] + [p.grad for p in loose])
+            cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
+            late = [ar for ar in live if ar.reduce_works is None]
+            self.grad_reducer.reduce([ar.grad for ar in late] + [p.grad for p in loose])
+            for ar in live:
+                ar.reduce_hook = None
+                if ar.reduce_works is not None:        # launched from the backward pass, overlapped with it
+                    works, comm = ar.reduce_works
+                    for w in works:
+                        w.wait()
+                    cur.wait_stream(comm)
+                    ar.reduce_works = None
         for ar in live:
             st = self._state_for(ar, ar.flat)
             GF._call(ar.flat, "ganffn_adam_step_dev", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel,

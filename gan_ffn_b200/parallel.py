@@ -45,6 +45,7 @@ class GradReducer:
         self.world_size = dist.get_world_size(group)
         self.bytes_reduced = 0
         self.calls = 0
+        self._streams = {}
 
     def reduce(self, buffers: Sequence[torch.Tensor]) -> None:
         works = []
@@ -54,6 +55,50 @@ class GradReducer:
             self.calls += 1
         for w in works:
             w.wait()
+
+    def reduce_arena_by_layer(self, arena, nlayers: int, bwd_stream: torch.cuda.Stream):
+        """All-reduce of one network's gradient arena in per-encoder-layer buckets, each launched as soon as that
+        layer's gradients are complete (``ganffn_net_bwd_layer_wait``), so the collective of layer l overlaps the
+        backward pass of layers l-1 .. 0 instead of sitting exposed in front of the optimizer.
+        Called right after ``ganffn_net_bwd`` was issued on ``bwd_stream``; everything is device-side (capturable).
+        Returns the async work handles (``FusedAdam.step`` waits on them) plus the communication stream to join."""
+        from ._lib import lib
+        comm = self._comm_stream(arena.grad.device)
+        tab, flat = arena.table, arena.grad
+        starts = [int(tab[l * 12]) for l in range(nlayers)] + [int(tab[nlayers * 12])]
+        works = []
+        L = lib()
+        whole = False
+        for l in range(nlayers - 1, 0, -1):
+            if not whole and L.cdll.ganffn_net_bwd_layer_wait(bwd_stream.cuda_stream, l, comm.cuda_stream) != 0:
+                comm.wait_stream(bwd_stream)        # no per-layer events: every bucket waits for the whole pass
+                whole = True
+            with torch.cuda.stream(comm):
+                works.append(dist.all_reduce(flat[starts[l]:starts[l + 1]], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        comm.wait_stream(bwd_stream)                # layer 0 and the head (+ `object`) are complete with the pass itself
+        with torch.cuda.stream(comm):
+            works.append(dist.all_reduce(flat[starts[0]:starts[1]], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            works.append(dist.all_reduce(flat[starts[nlayers]:], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.bytes_reduced += flat.numel() * flat.element_size()
+        self.calls += len(works)
+        return works, comm
+
+    def reduce_arena_whole(self, arena, after_stream: torch.cuda.Stream):
+        """One all-reduce of a whole gradient arena on the communication stream, ordered after ``after_stream``."""
+        comm = self._comm_stream(arena.grad.device)
+        comm.wait_stream(after_stream)
+        with torch.cuda.stream(comm):
+            works = [dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
+        self.bytes_reduced += arena.grad.numel() * arena.grad.element_size()
+        self.calls += 1
+        return works, comm
+
+    def _comm_stream(self, device) -> torch.cuda.Stream:
+        st = self._streams.get(device.index)
+        if st is None:
+            st = torch.cuda.Stream(device=device)
+            self._streams[device.index] = st
+        return st
 
     def global_sum(self, value: float, device) -> float:
         """Sum of a host scalar over the group (e.g. dialogues per rank -> global batch size)."""

@@ -139,6 +139,12 @@ class GANTrainer:
         if self.grad_reducer is not None:
             adv.scale_tensor = self.grad_reducer.local_fraction_tensor(batch_size, real_text.device)
         disc_step = train_disc_batched if self.batch_disc else train_disc
+        for o in (self.opt_acoustic_D, self.opt_visual_D, self.opt_text_D):
+            o.expected_backwards = 1 if self.batch_disc else 2     # the two-pass body adds D(real) and D(fake) into one arena
+        if self.batch_disc:                                         # the network pass, then the separate `object` projection
+            self.opt_visual_D.expected_backwards, self.opt_visual_D.sequential_backwards = 2, True
+        else:
+            self.opt_visual_D.sequential_backwards = False
 
         def run(kind, d, g):
             if kind == "D":

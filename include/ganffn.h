@@ -223,6 +223,13 @@ int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const floa
                    float* dx, float* scratch, int S, int B, int d_in, int d, int nhead, int dff,
                    int nlayers, int h1, int h2, int train, float p_head, uint64_t seed,
                    const uint64_t* seed_dev, int accumulate, void* stream);
+/* Per-layer gradient completion, for overlapping the data-parallel all-reduce with the rest of the backward pass
+ * ("bucket per encoder layer and launch as each layer's weight-grad completes"): makes
+ * `waiting_stream` wait, on the device, until every gradient of encoder layer `layer` written by the LAST
+ * ganffn_net_bwd issued on `bwd_stream` has landed.  Layers complete from nlayers-1 down to 0; the head gradients and
+ * layer 0 are complete when ganffn_net_bwd's own work on `bwd_stream` is.  Returns GANFFN_ERR_ARG when no per-layer
+ * event exists (side streams off): wait for the whole pass instead. */
+int ganffn_net_bwd_layer_wait(void* bwd_stream, int layer, void* waiting_stream);
 /* Both return -1 when the shape violates a precondition (ganffn_last_error() says which). */
 int64_t ganffn_net_stash_floats(int kind, int S, int B, int d_in, int d, int nhead, int dff,
                                 int nlayers, int h1, int h2);
