@@ -259,6 +259,9 @@ def run_ours(args):
                            overlap=not args.no_lanes, batch_disc=not args.no_batch_disc, chains=args.chains)
     cls = train.ClassifierTrainer(ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev), grad_reducer=reducer,
                                   overlap=not args.no_lanes)
+    if args.no_overlap_reduce:
+        for o in (gan.opt_acoustic_G, gan.opt_acoustic_D, gan.opt_visual_G, gan.opt_visual_D, gan.opt_text_G, gan.opt_text_D, cls.optimizer):
+            o.overlap_reduce = False
     G.manual_seed(3407 + rank)
 
     S, B = args.seq_len, args.dialogues
@@ -339,7 +342,7 @@ def run_ours(args):
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "quick": True,
                               "stage1_ms": stage1_ms, "stage2_ms": stage2_ms, "e2e": e2e_value, "gpu_launches": launches,
-                              "lanes": not args.no_lanes, "batch_disc": not args.no_batch_disc, "chains": args.chains,
+                              "lanes": not args.no_lanes, "batch_disc": not args.no_batch_disc, "chains": args.chains, "overlap_reduce": not args.no_overlap_reduce,
                               "wgrad_cap": os.environ.get("GANFFN_WGRAD_CAP"), "clocks": clocks}), flush=True)
         if world > 1 and not parallel.shutdown([stepper]):
             os._exit(0)
@@ -567,6 +570,7 @@ def main():
     ap.add_argument("--graph-utterances", type=int, default=1_000_000)
     ap.add_argument("--no-lanes", action="store_true", help="A/B switch: run the networks of a loop body serially (no concurrent lanes)")
     ap.add_argument("--no-batch-disc", action="store_true", help="A/B switch: train_disc as two discriminator passes (reference body) instead of one [real|fake] pass")
+    ap.add_argument("--no-overlap-reduce", action="store_true", help="A/B switch: one gradient all-reduce per arena at optimizer.step() instead of per-layer buckets overlapped with the backward pass")
     ap.add_argument("--chains", type=int, default=2, help="A/B switch: concurrent sub-step chains of the stage-1 batch (1 = serial order)")
     ap.add_argument("--quick", action="store_true", help="headline + e2e only: skip the roofline, Adam, graph, CPU and eager-GPU legs (A/B runs)")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")

@@ -975,7 +975,11 @@ TcPlan tc_plan_atomic(int M, int N, int K) {
   Cand cands[64];
   int n = 0;
   double best_latency = 1e300;
-  for (int sp = 1; sp <= nkb && sp <= 64; ++sp) {
+  // candidates start at the smallest split that respects the 128-accumulation chain cap (kps <= 1024): a reduction
+  // over a million rows (the graph layers' weight gradients on the 1M-utterance sweep, K = 1 000 030) needs ~1000
+  // slices -- r2: with the old "sp <= 64" scan no candidate qualified and the product ran on 7 CTAs for 13 ms
+  const int sp_min = std::max(1, cdiv(K, 1024));
+  for (int sp = sp_min; sp <= nkb && sp < sp_min + 64 && n < 64; ++sp) {
     const int kps = (int)round_up(cdiv(K, sp), BK);
     if (kps > 1024) continue;
     const int splits = cdiv(K, kps);

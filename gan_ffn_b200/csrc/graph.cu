@@ -11,6 +11,7 @@
 //   * gather: one warp per node.  Lane c owns one float4 of the feature row, so every neighbour row is one coalesced
 //     400-byte (d=100) read; neighbour rows are re-read by <= wp+wf+1 nodes of the same dialogue, i.e. from L2.
 //     The backward "scatter-add" runs on the transposed CSR as the same gather: no atomics, deterministic.
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace ganffn {
@@ -374,7 +375,100 @@ __global__ void __launch_bounds__(256) graph_gather_dialogue_kernel(const float*
   }
 }
 
+// ---- plain (GraphConv) sum over a window graph: running window sums -------------------------------------------------
+// The rows of a window graph are contiguous runs [lo_i, hi_i] with lo and hi non-decreasing in i, so
+//   out_i = out_{i-1} + sum_{hi_{i-1} < j <= hi_i} x_j - sum_{lo_{i-1} <= j < lo_i} x_j :
+// two row updates per node instead of wp + wf + 1 neighbour reads (r1's dialogue-staged gather was instruction-issue
+// bound at 32 % of the HBM roofline doing 21 shared-memory adds per output float4).  One CTA = one dialogue staged in
+// shared memory; thread = (row segment, float4 column): the first row of a segment is summed directly, the rest slide.
+// A row that is not a contiguous run, or whose bounds move backwards, is summed directly from the CSR (generic graphs
+// stay correct).  Sums differ from the direct sum by the rounding of <= L/segments running updates (~1e-6 relative).
+__global__ void __launch_bounds__(256) graph_gather_window_kernel(const float* __restrict__ x, const int64_t* __restrict__ node_off,
+                                                                  const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                                                  float* __restrict__ out, int d4) {
+  extern __shared__ __align__(16) float4 xs[];   // [L][d4], then int2 bounds[L] (lo, hi; hi < lo marks a non-run row)
+  const int b = blockIdx.x;
+  const int64_t n0 = node_off[b];
+  const int L = (int)(node_off[b + 1] - n0);
+  const float4* xv = reinterpret_cast<const float4*>(x) + n0 * d4;
+  int2* bounds = reinterpret_cast<int2*>(xs + (size_t)L * d4);
+  {
+    const int total = L * d4, step = blockDim.x;
+    int idx = threadIdx.x;
+    for (; idx + 3 * step < total; idx += 4 * step) {
+      const float4 a0 = __ldg(xv + idx), a1 = __ldg(xv + idx + step), a2 = __ldg(xv + idx + 2 * step), a3 = __ldg(xv + idx + 3 * step);
+      xs[idx] = a0; xs[idx + step] = a1; xs[idx + 2 * step] = a2; xs[idx + 3 * step] = a3;
+    }
+    for (; idx < total; idx += step) xs[idx] = __ldg(xv + idx);
+  }
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const int64_t beg = rowptr[n0 + i], end = rowptr[n0 + i + 1];
+    int lo = 0, hi = -1;
+    if (end > beg) {
+      lo = col[beg] - (int)n0;
+      hi = col[end - 1] - (int)n0;
+      if (hi - lo != (int)(end - beg) - 1 || lo < 0 || hi >= L) { lo = 1; hi = -1; }   // not a run inside the dialogue
+    } else {
+      lo = 0; hi = -2;                                                                  // empty row: sum = 0
+    }
+    bounds[i] = make_int2(lo, hi);
+  }
+  __syncthreads();
+  const int groups = max(1, (int)blockDim.x / d4);
+  const int g = threadIdx.x / d4, c = threadIdx.x % d4;
+  if (g >= groups) return;
+  const int seg = (L + groups - 1) / groups;
+  const int i_beg = g * seg, i_end = min(L, i_beg + seg);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int plo = 0, phi = -1;
+  bool have = false;
+  for (int i = i_beg; i < i_end; ++i) {
+    const int2 bd = bounds[i];
+    const int64_t n = n0 + i;
+    if (bd.y == -2) {                        // empty row
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      have = false;
+    } else if (bd.y < bd.x) {                // generic row: direct sum over the CSR entries
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t e = rowptr[n]; e < rowptr[n + 1]; ++e) {
+        const int64_t j = col[e];
+        const float4 v = (j >= n0 && j < n0 + L) ? xs[(j - n0) * d4 + c] : __ldg(reinterpret_cast<const float4*>(x) + j * d4 + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      have = false;
+    } else if (have && bd.x >= plo && bd.y >= phi && bd.x <= phi + 1) {   // slide
+      for (int j = phi + 1; j <= bd.y; ++j) { const float4 v = xs[j * d4 + c]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      for (int j = plo; j < bd.x; ++j) { const float4 v = xs[j * d4 + c]; acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w; }
+      plo = bd.x; phi = bd.y;
+    } else {                                 // first row of the segment (or a jump): direct sum of the run
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = bd.x; j <= bd.y; ++j) { const float4 v = xs[j * d4 + c]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      plo = bd.x; phi = bd.y; have = true;
+    }
+    reinterpret_cast<float4*>(out)[n * d4 + c] = acc;
+  }
+}
+
 constexpr size_t GATHER_SMEM_MAX = 200 * 1024;
+
+int launch_gather_window(const float* x, const int64_t* node_off, int B, int max_len, const int64_t* rowptr, const int* col,
+                         float* out, int d, cudaStream_t st) {
+  const size_t smem = (size_t)max_len * d * sizeof(float) + (size_t)max_len * sizeof(int2);
+  {
+    static std::atomic<unsigned long long> done{0ull};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+      cudaFuncSetAttribute(graph_gather_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GATHER_SMEM_MAX + 2048));
+      cudaFuncSetAttribute(graph_gather_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      done.fetch_or(bit, std::memory_order_release);
+    }
+  }
+  graph_gather_window_kernel<<<B, 256, smem, st>>>(x, node_off, rowptr, col, out, d / 4);
+  GANFFN_LAUNCHED("graph_gather_window_kernel");
+  return GANFFN_OK;
+}
 
 template <bool TYPED, int NV>
 int launch_gather_dialogue(const float* x, const int64_t* node_off, int B, int max_len, const int64_t* rowptr, const int* col,
@@ -461,6 +555,10 @@ int graph_gather_sum(const float* in, const int64_t* rowptr, const int* col, con
   if (N <= 0) return GANFFN_OK;
   const dim3 grid(cdiv(N, 8));
   const bool typed = in_slots > 1, weighted = inv_cnt != nullptr;
+  static const bool no_window = getenv("GANFFN_NO_WINDOW_SUM") != nullptr;   // A/B switch
+  if (!typed && !weighted && !no_window && node_off && B > 0 && max_len > 0 && d / 4 <= 256 &&
+      (size_t)max_len * d * sizeof(float) <= GATHER_SMEM_MAX)
+    return launch_gather_window(in, node_off, B, max_len, rowptr, col, out, d, st);
   if (!typed && !weighted && node_off && B > 0 && max_len > 0 && (size_t)max_len * d * sizeof(float) <= GATHER_SMEM_MAX)
     return d <= 128 ? launch_gather_dialogue<false, 1>(in, node_off, B, max_len, rowptr, col, etype, inv_cnt, out, R, d, st)
                     : launch_gather_dialogue<false, GV>(in, node_off, B, max_len, rowptr, col, etype, inv_cnt, out, R, d, st);

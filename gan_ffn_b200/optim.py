@@ -84,6 +84,7 @@ class FusedAdam:
                 # the all-reduce itself, layer by layer (functional._NetFunction.backward -> GradReducer.reduce_arena_by_layer)
                 ar.reduce_hook = ({"reducer": self.grad_reducer, "expected": int(self.expected_backwards), "seen": 0}
                                   if (self.grad_reducer is not None and self.overlap_reduce and ar.grad.is_cuda and
+                                      ar.numel >= getattr(self.grad_reducer, "overlap_min_numel", 0) and
                                       (self.expected_backwards == 1 or self.sequential_backwards)) else None)
 
     def _state_for(self, key, like: torch.Tensor):

@@ -38,7 +38,12 @@ def shard_batch(batch: Batch, world_size: int, rank: int) -> Batch:
 class GradReducer:
     """Sum-all-reduce of flat gradient buffers across the data-parallel group."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, overlap_min_numel: int = 8_000_000):
+        # Per-layer overlapped all-reduce only for arenas of at least this many parameters (the visual generator's
+        # 25.8 M: 12.6 MB buckets).  Measured at 2 GPUs (r2): bucketing the 3.6-4.1 M-parameter d=100 networks too adds
+        # ~150 small NCCL launches per step that fight the one-CTA-per-SM GEMM kernels for SMs (59.0 vs 57.8 ms/step);
+        # their single 14.5 MB all-reduce already overlaps the other sub-step chain.
+        self.overlap_min_numel = overlap_min_numel
         if not dist.is_initialized():
             raise RuntimeError("GradReducer needs torch.distributed to be initialised (one process per GPU)")
         self.group = group

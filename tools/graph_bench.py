@@ -65,7 +65,48 @@ def graph_leg(utterances=1_000_000, d=100, wp=10, wf=10, reps=5, device="cuda"):
         L.call("ganffn_graph_gather_sum", ptr(x), ptr(g.rowptr), ptr(g.col), None, None, ptr(dx), N, 1, R, d, ptr(g.node_off), g.B, g.S, st)
     ms = timed(plain)
     by = N * d * 4 + E * 4 + N * 8 + N * d * 4                             # x once, CSR, out
-    out["graphconv_gather"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6}
+    out["graphconv_gather"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6,
+                               "kernel": "running window sums (two row updates per node); reads only the first / last col of a row"}
+
+    # ---- whole layers: the kernel-level figures above count each kernel's own input + output, and the typed gather's
+    # output [N, n_rel*d] is an INTERMEDIATE of the RGCN layer (it exists because gather and contraction are two
+    # launches).  Per SURVEY.md §8(d) the honest algorithmic bytes of a layer are its inputs + final output only:
+    # x + CSR + inv_cnt + out[N,h].  The layer also does 2*N*(n_rel+1)*d*h FLOP of dense contraction, which makes
+    # the RGCN layer tensor-bound once fused (~310 FLOP per honest byte) -- both fractions are reported.
+    from gan_ffn_b200.graph import GraphConv, RGCNConv
+    h = d
+    torch.manual_seed(0)
+    rg, gc = RGCNConv(d, h, R).to(dev), GraphConv(d, h).to(dev)
+    peaks0 = {}
+    try:
+        peaks0 = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_ceiling = float(peaks0.get("bf16_tflops", 1600.0)) / 6.0           # 3xTF32 on the tf32 pipe
+    with torch.no_grad():
+        ms = timed(lambda: rg(x, g))
+    by = N * d * 4 + E * 8 + N * 8 + N * R * 4 + N * h * 4
+    fl = 2.0 * N * (R + 1) * d * h
+    out["rgcn_layer_fwd"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6, "gflop": fl / 1e9, "tflops": fl / ms / 1e9,
+                             "frac_of_3xtf32_ceiling": fl / ms / 1e9 / tf_ceiling, "bound": "tensor (fp32-parity 3xTF32)",
+                             "launches": "typed gather + root product + relation product"}
+    with torch.no_grad():
+        ms = timed(lambda: gc(x, g))
+    by = N * d * 4 + E * 4 + N * 8 + N * h * 4
+    fl = 2.0 * N * 2 * d * h
+    out["graphconv_layer_fwd"] = {"ms": ms, "algorithmic_bytes": by, "GBps": by / ms / 1e6, "gflop": fl / 1e9, "tflops": fl / ms / 1e9,
+                                  "frac_of_3xtf32_ceiling": fl / ms / 1e9 / tf_ceiling, "bound": "hbm / tensor (about even)",
+                                  "launches": "window-sum gather + two products"}
+    xg = x.clone().requires_grad_(True)
+    def rg_fb():
+        y = rg(xg, g)
+        y.backward(torch.ones_like(y))
+        xg.grad = None
+    ms = timed(rg_fb)
+    out["rgcn_layer_fwd_bwd"] = {"ms": ms, "gflop": 3 * 2.0 * N * (R + 1) * d * h / 1e9, "tflops": 3 * 2.0 * N * (R + 1) * d * h / ms / 1e9,
+                                 "algorithmic_bytes": 2 * (N * d * 4 + N * h * 4) + 2 * (E * 8 + N * 8 + N * R * 4),
+                                 "GBps": (2 * (N * d * 4 + N * h * 4) + 2 * (E * 8 + N * 8 + N * R * 4)) / ms / 1e6}
+    del rg, gc, xg
 
     peaks = {}
     try:
@@ -74,7 +115,8 @@ def graph_leg(utterances=1_000_000, d=100, wp=10, wf=10, reps=5, device="cuda"):
         pass
     peak = float(peaks.get("hbm_gbs", 6500.0))
     for v in out.values():
-        v["frac_of_hbm_peak"] = v["GBps"] / peak
+        if "GBps" in v:
+            v["frac_of_hbm_peak"] = v["GBps"] / peak
     return {"workload": f"{N} utterances in {B} dialogues of 10..110 turns, window {wp}/{wf}, 2 speakers, d={d}: {E} edges, {R} relations",
             "hbm_peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6500 GB/s",
             "parity": "unpinned: no reference implementation (SURVEY.md D1/D2); checked against oracle/graph_oracle.py",
