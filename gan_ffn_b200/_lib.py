@@ -14,7 +14,8 @@ from typing import Dict, List, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ganffn.h")
-LIB_PATH = os.path.join(_HERE, "libganffn.so")
+# GANFFN_LIB: tuning aid only (A/B runs of a variant build made by tools/build_variant.sh)
+LIB_PATH = os.environ.get("GANFFN_LIB") or os.path.join(_HERE, "libganffn.so")
 
 _CTYPES = {
     "int": ctypes.c_int,

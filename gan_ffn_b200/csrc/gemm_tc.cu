@@ -38,7 +38,10 @@ constexpr int NPW = NAW + NBW;
 constexpr int NB = NBW * 32;            // B producer threads
 constexpr int NTHREADS = (NPW + 1) * 32;
 constexpr int STAGES = 4;
-constexpr int RING = 3;                 // K blocks each producer thread keeps in flight in registers
+#ifndef GANFFN_TC_RING
+#define GANFFN_TC_RING 3
+#endif
+constexpr int RING = GANFFN_TC_RING;    // K blocks each producer thread keeps in flight in registers
 constexpr int B_TILE = BN * BK * 4;     // bytes of one B tile (hi or lo)
 constexpr int STAGE = 2 * B_TILE;
 constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -1005,7 +1008,7 @@ TcPlan tc_plan(int M, int N, int K) {
   const int nkb = cdiv(K, BK);
   TcPlan best{1, (int)round_up(K, BK)};
   double best_cost = 1e300;
-  const int cand_splits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+  const int cand_splits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, std::max(33, cdiv(K, 1024))};   // last: chain cap for huge K
   for (int sp : cand_splits) {
     if (sp > 1 && nkb / sp < 4) continue;
     const int kps = (int)round_up(cdiv(K, sp), BK);
