@@ -256,7 +256,8 @@ def run_ours(args):
     nets, ffn = train.build_networks(device=dev)
     gan = train.GANTrainer(nets["acoustic_gen"], nets["visual_gen"], nets["text_gen"], nets["acoustic_disc"],
                            nets["visual_disc"], nets["text_disc"], grad_reducer=reducer, world_size=world,
-                           overlap=not args.no_lanes, batch_disc=not args.no_batch_disc, chains=args.chains)
+                           overlap=not args.no_lanes, batch_disc=not args.no_batch_disc, chains=args.chains,
+                           freeze_disc=not args.no_freeze_disc)
     cls = train.ClassifierTrainer(ffn, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device=dev), grad_reducer=reducer,
                                   overlap=not args.no_lanes)
     if args.no_overlap_reduce:
@@ -342,7 +343,7 @@ def run_ours(args):
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "quick": True,
                               "stage1_ms": stage1_ms, "stage2_ms": stage2_ms, "e2e": e2e_value, "gpu_launches": launches,
-                              "lanes": not args.no_lanes, "batch_disc": not args.no_batch_disc, "chains": args.chains, "overlap_reduce": not args.no_overlap_reduce,
+                              "lanes": not args.no_lanes, "batch_disc": not args.no_batch_disc, "freeze_disc": not args.no_freeze_disc, "chains": args.chains, "overlap_reduce": not args.no_overlap_reduce,
                               "wgrad_cap": os.environ.get("GANFFN_WGRAD_CAP"), "clocks": clocks}), flush=True)
         if world > 1 and not parallel.shutdown([stepper]):
             os._exit(0)
@@ -570,6 +571,7 @@ def main():
     ap.add_argument("--graph-utterances", type=int, default=1_000_000)
     ap.add_argument("--no-lanes", action="store_true", help="A/B switch: run the networks of a loop body serially (no concurrent lanes)")
     ap.add_argument("--no-batch-disc", action="store_true", help="A/B switch: train_disc as two discriminator passes (reference body) instead of one [real|fake] pass")
+    ap.add_argument("--no-freeze-disc", action="store_true", help="A/B switch: train_gen computes the discriminator's (never read) weight gradients, as the reference body does")
     ap.add_argument("--no-overlap-reduce", action="store_true", help="A/B switch: one gradient all-reduce per arena at optimizer.step() instead of per-layer buckets overlapped with the backward pass")
     ap.add_argument("--chains", type=int, default=2, help="A/B switch: concurrent sub-step chains of the stage-1 batch (1 = serial order)")
     ap.add_argument("--quick", action="store_true", help="headline + e2e only: skip the roofline, Adam, graph, CPU and eager-GPU legs (A/B runs)")

@@ -8,9 +8,9 @@ from .model import (AcousticDiscriminator, AcousticGenerator, BCELoss, GAN_FFN, 
                     PositionalEncoding,
                     TextDiscriminator, TextGenerator, VisualDiscriminator, VisualGenerator)
 from .optim import FusedAdam
-from .functional import manual_seed, set_deterministic
+from .functional import frozen_parameters, manual_seed, set_deterministic
 from .checkpoint import load_reference_state, strip_data_parallel
 
 __all__ = ["AcousticGenerator", "VisualGenerator", "TextGenerator", "AcousticDiscriminator", "VisualDiscriminator",
            "TextDiscriminator", "GAN_FFN", "GAN_FFN_DialogueRNN", "MaskedNLLLoss", "BCELoss", "PositionalEncoding", "FusedAdam",
-           "manual_seed", "set_deterministic", "load_reference_state", "strip_data_parallel"]
+           "manual_seed", "set_deterministic", "frozen_parameters", "load_reference_state", "strip_data_parallel"]

@@ -25,7 +25,8 @@ struct Cfg {
   static constexpr int CWV = (CW % 4 == 0) ? 4 : 1;
 };
 
-// Cooperative copy of one head's [S, HD] slice (row stride `ld` floats in global) to smem [S][HD].
+// Cooperative asynchronous copy (cp.async, see common.cuh) of one head's [S, HD] slice (row stride `ld` floats in
+// global) to smem [S][HD]; the caller runs cp_async_wait_all() before the __syncthreads() that publishes the tile.
 template <int HD>
 __device__ __forceinline__ void load_tile(const float* __restrict__ g, int ld, float* s, int S) {
   constexpr int W = Cfg<HD>::W, CPR = HD / W;
@@ -33,9 +34,9 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ g, int ld, f
     const int r = idx / CPR, c = (idx % CPR) * W;
     const float* src = g + (size_t)r * ld + c;
     float* dst = s + r * HD + c;
-    if (W == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
-    else if (W == 2) *reinterpret_cast<float2*>(dst) = __ldg(reinterpret_cast<const float2*>(src));
-    else *dst = __ldg(src);
+    if (W == 4) cp_async_16(dst, src);
+    else if (W == 2) cp_async_8(dst, src);
+    else cp_async_4(dst, src);
   }
 }
 
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_fwd_kernel(const f
   load_tile<HD>(base, ld, Qs, S);
   load_tile<HD>(base + d, ld, Ks, S);
   load_tile<HD>(base + 2 * d, ld, Vs, S);
+  cp_async_wait_all();
   __syncthreads();
 
   const int nrw = (S + 31) >> 5;                       // row warps per group
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
   load_tile<HD>(base + d, ld, Ks, S);
   load_tile<HD>(base + 2 * d, ld, Vs, S);
   load_tile<HD>(dobase, ldo, dOs, S);
+  cp_async_wait_all();
   __syncthreads();
   {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(NG * 32, 5) attention_fwd_small_kernel(const f
   const float scale = rsqrtf((float)HD);
   float q[HD];
   row_to_regs<HD>(base + (size_t)ir * ld, q, scale);   // the thread's own query row straight from global memory
+  cp_async_wait_all();
   __syncthreads();
 
   float s[KPG];
@@ -503,6 +507,7 @@ __global__ void __launch_bounds__(NG * 32, 5) attention_bwd_small_kernel(
     Ds[r] = dot_regs<HD>(drow, orow);
     Ls[r] = lse[(size_t)bh * S + r];
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;

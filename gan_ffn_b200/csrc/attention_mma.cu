@@ -56,22 +56,32 @@ struct Dims {
   static constexpr int W = (HD % 4 == 0) ? 4 : (HD % 2 == 0) ? 2 : 1;
 };
 
-// [S, HD] slice of one head (row stride ld floats in global) -> smem [rows][LD], zero padded to `rows` x HDP
+// [S, HD] slice of one head (row stride ld floats in global) -> smem [rows][LD], zero padded to `rows` x HDP.
+// Asynchronous (cp.async, common.cuh): every chunk of the tile is in flight at once instead of one exposed global
+// latency per loop iteration; the caller runs cp_async_wait_all() + __syncthreads() (and scale_head for Q) afterwards.
 template <int HD>
-__device__ __forceinline__ void load_head(const float* __restrict__ g, int ld, float* s, int S, int rows, float mul) {
+__device__ __forceinline__ void load_head(const float* __restrict__ g, int ld, float* s, int S, int rows) {
   constexpr int LD = Dims<HD>::LD, HDP = Dims<HD>::HDP, W = Dims<HD>::W, CPR = HDP / W;
+  static_assert(LD % W == 0, "cp.async destination alignment");
   for (int idx = threadIdx.x; idx < rows * CPR; idx += blockDim.x) {
     const int r = idx / CPR, c = (idx % CPR) * W;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float* dst = s + r * LD + c;
     if (r < S && c < HD) {
       const float* src = g + (size_t)r * ld + c;
-      if (W == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-      else if (W == 2) { const float2 q = __ldg(reinterpret_cast<const float2*>(src)); v[0] = q.x; v[1] = q.y; }
-      else v[0] = __ldg(src);
-    }
+      if (W == 4) cp_async_16(dst, src);
+      else if (W == 2) cp_async_8(dst, src);
+      else cp_async_4(dst, src);
+    } else {
 #pragma unroll
-    for (int j = 0; j < W; ++j) s[r * LD + c + j] = v[j] * mul;
+      for (int j = 0; j < W; ++j) dst[j] = 0.f;
+    }
   }
+}
+// in-place scaling of a staged tile (Q is kept pre-multiplied by 1/sqrt(head_dim)); between two __syncthreads()
+template <int HD>
+__device__ __forceinline__ void scale_head(float* s, int rows, float mul) {
+  constexpr int LD = Dims<HD>::LD, HDP = Dims<HD>::HDP;
+  for (int idx = threadIdx.x; idx < rows * HDP; idx += blockDim.x) s[(idx / HDP) * LD + idx % HDP] *= mul;
 }
 
 // A fragments (hi, lo) of 16 rows starting at row0 of a [rows][LD] smem tile, all KS k-steps
@@ -151,9 +161,12 @@ __global__ void __launch_bounds__(224) attention_fwd_mma_kernel(const float* __r
   const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
   const int ld = B * 3 * d;
   const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
-  load_head<HD>(base, ld, Qs, S, S16, rsqrtf((float)HD));
-  load_head<HD>(base + d, ld, Ks, S, S8, 1.f);
-  load_head<HD>(base + 2 * d, ld, Vs, S, S8, 1.f);
+  load_head<HD>(base, ld, Qs, S, S16);
+  load_head<HD>(base + d, ld, Ks, S, S8);
+  load_head<HD>(base + 2 * d, ld, Vs, S, S8);
+  cp_async_wait_all();
+  __syncthreads();
+  scale_head<HD>(Qs, S16, rsqrtf((float)HD));
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -251,10 +264,10 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
   const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
   const float* obase = o + (size_t)b * d + (size_t)h * HD;
   const float* dobase = d_o + (size_t)b * d + (size_t)h * HD;
-  load_head<HD>(base, ld, Qs, S, S16, scale);
-  load_head<HD>(base + d, ld, Ks, S, S16, 1.f);
-  load_head<HD>(base + 2 * d, ld, Vs, S, S16, 1.f);
-  load_head<HD>(dobase, ldo, dOs, S, S16, 1.f);
+  load_head<HD>(base, ld, Qs, S, S16);
+  load_head<HD>(base + d, ld, Ks, S, S16);
+  load_head<HD>(base + 2 * d, ld, Vs, S, S16);
+  load_head<HD>(dobase, ldo, dOs, S, S16);
   for (int r = threadIdx.x; r < S16; r += blockDim.x) {
     float acc = 0.f, l = 0.f;
     if (r < S) {
@@ -278,6 +291,9 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
     Ds[r] = acc;
     Ls[r] = l;
   }
+  cp_async_wait_all();
+  __syncthreads();
+  scale_head<HD>(Qs, S16, scale);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;

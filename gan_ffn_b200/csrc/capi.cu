@@ -74,7 +74,9 @@ int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_i
   } else {
     Epilogue e2 = ep;
     e2.rowsum = nullptr;
+    e2.ln_out = nullptr;
     rc = gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, e2, scratch, scratch_floats, st);
+    if (rc == GANFFN_OK && ep.ln_out) rc = layernorm_fwd(C, ep.ln_gamma, ep.ln_beta, ep.ln_out, M, N, st);   // not fused on the FFMA engine
   }
   if (g_prof) {
     prof_record(pe.b, st);
@@ -185,6 +187,18 @@ int ganffn_linear_fwd(const float* x, const float* w, const float* bias, const f
   ep.bias = bias; ep.residual = residual; ep.ldr = N; ep.pre = pre; ep.act = act; ep.drop_before_act = drop_before_act;
   ep.p_drop = p_drop; ep.seed = seed; ep.site = (uint32_t)site;
   return gemm(x, K, false, w, K, true, y, N, M, N, K, ep, scratch, scratch_floats, S(stream));
+}
+
+int ganffn_linear_ln_fwd(const float* x, const float* w, const float* bias, const float* residual, const float* gamma,
+                         const float* beta, float* z, float* y, int M, int N, int K, float p_drop, uint64_t seed, int site,
+                         float* scratch, int64_t scratch_floats, void* stream) {
+  GANFFN_CHECK_ARG(x && w && bias && residual && gamma && beta && z && y, "linear_ln_fwd: null pointer");
+  GANFFN_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "linear_ln_fwd: dropout p=%f", p_drop);
+  GANFFN_CHECK_ARG(N % 4 == 0 && N <= 512, "linear_ln_fwd: N=%d must be a multiple of 4 and <= 512 (LayerNorm width)", N);
+  Epilogue ep;
+  ep.bias = bias; ep.residual = residual; ep.ldr = N; ep.p_drop = p_drop; ep.seed = seed; ep.site = (uint32_t)site;
+  ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_out = y;
+  return gemm(x, K, false, w, K, true, z, N, M, N, K, ep, scratch, scratch_floats, S(stream));
 }
 
 int ganffn_linear_dgrad(const float* dy, const float* w, const float* residual, float* dx, int M, int N, int K,

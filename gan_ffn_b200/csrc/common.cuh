@@ -157,6 +157,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS) ---------------------------------------------------------------
+// The attention kernels stage a dialogue's Q/K/V/dO head slices (rows of 8..64 floats at a stride of B*3*d floats) in
+// shared memory.  Through registers that is a loop of dependent LDG -> STS pairs, i.e. one exposed global-memory
+// latency per iteration (r2 ncu of attention_fwd_small_kernel: 38 % of the stall cycles were long-scoreboard waits of
+// the eight tile-load iterations); with cp.async every chunk of the tile is in flight at once.
+__device__ __forceinline__ void cp_async_8(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- GEMM epilogue shared by the SIMT and tcgen05 engines --------------------------------------
 // Backward-activation codes (dact)
 enum { DACT_NONE = 0, DACT_NONZERO = 1, DACT_GELU = 2 };
@@ -182,6 +198,13 @@ struct Epilogue {
   // or its direct epilogue) and ignores `rowsum`.
   int atomic_acc = 0;
   float* rowsum = nullptr;
+  // LayerNorm behind the epilogue (post-norm encoder layer: x = LN(residual + drop(linear(..)))).  When ln_out is set,
+  // gemm() also writes ln_out[m, :] = LN(C[m, :]) * ln_gamma + ln_beta (row stride ldc, needs ldc == N).  The tcgen05
+  // engine does it inside the GEMM kernel when one tile spans the row (N <= 128) or inside the split-K fold; every
+  // other case runs the stand-alone LayerNorm kernel after the product.
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float* ln_out = nullptr;
 };
 
 // Applies the epilogue to the four accumulators of row m, columns n..n+3 (n % 4 == 0) and

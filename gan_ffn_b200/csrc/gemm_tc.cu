@@ -318,6 +318,7 @@ __device__ __forceinline__ void epi_vec(const TcParams& p, uint32_t stage, int m
     dscale = 1.0f / (1.0f - ep.p_drop);
   }
   const float dact_scale = ep.dact_scale;
+  const bool ln_after = ep.ln_out != nullptr;
   // all eight row groups of the residual / activation source are requested up front: one memory latency per
   // sub-tile instead of one per row group (the dH = dZ W2 product reads 24.6 MB of h here)
   float4 aux[8];
@@ -357,11 +358,57 @@ __device__ __forceinline__ void epi_vec(const TcParams& p, uint32_t stage, int m
         for (int j = 0; j < 4; ++j) v[j] += ax[j];
       }
       *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+      if (RES && BIAS && ln_after)   // the fused LayerNorm reads the finished rows from the staging tiles (epilogue_layernorm)
+        sts128(sptr, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
     }
     cptr += cstep;
     sptr += 4 * 36 * 4;
     rows_left -= 4;
     if (DROP) z += zstep;
+  }
+}
+
+// ---- LayerNorm fused behind the epilogue (one tile spans the row: N <= 128) ----------------------------------------------
+// The four warps of a lane quadrant (32 rows x 4 column groups) have written z = residual + drop(acc + bias) to global
+// memory and back into their staging tiles; after a named barrier over those 128 threads each warp normalises eight of
+// the 32 rows: lane = column within a 32-wide group, the same two-pass arithmetic as layernorm_fwd_kernel (rowwise.cu).
+constexpr float TC_LN_EPS = 1e-5f;
+__device__ __forceinline__ void epilogue_layernorm(const TcParams& p, uint32_t smem_base, int m_quad, int quad, int cg, int lane) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+  const Epilogue& ep = p.ep;
+  float gm[4], bt[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    gm[k] = c < p.N ? __ldg(ep.ln_gamma + c) : 0.f;
+    bt[k] = c < p.N ? __ldg(ep.ln_beta + c) : 0.f;
+  }
+  const float inv_n = 1.0f / (float)p.N;
+#pragma unroll 2
+  for (int rr = 0; rr < 8; ++rr) {
+    const int row = cg * 8 + rr, m = m_quad + row;
+    float v[4], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = 0.f;
+      if (lane + 32 * k < p.N) {
+        const uint32_t a = smem_base + (uint32_t)(((quad + 4 * k) * (32 * 36) + row * 36 + lane) * 4);
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(a) : "memory");
+      }
+      sum += v[k];
+    }
+    const float mean = warp_sum(sum) * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < p.N) { v[k] -= mean; sq += v[k] * v[k]; }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_n + TC_LN_EPS);
+    if (m < p.M) {
+      float* y = ep.ln_out + (size_t)m * p.ldc;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < p.N) y[lane + 32 * k] = v[k] * rstd * gm[k] + bt[k];
+    }
   }
 }
 
@@ -669,7 +716,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
     tc_fence_after();
     if (t == 0) TR(4);
     const int quad = warp & 3, col0 = (warp >> 2) * 32;
-    if (nkb > 0 && n0 + col0 < p.N) {
+    const bool live = nkb > 0 && n0 + col0 < p.N;
+    if (live) {
       const uint32_t stage = smem_u32(smem) + (uint32_t)(warp * (32 * 36) * 4);   // private 32 x 36 fp32 transpose buffer
       uint32_t r[32], rl[32];
       const uint32_t tr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
@@ -696,6 +744,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams p) 
       epilogue_subtile<EPI>(p, stage, m0 + quad * 32, n0 + col0, lane, blockIdx.z);
       if (t == 0) TR(72);
     }
+    // host side: only set for out_mode 0, one tile across N, and an epilogue served by epi_vec<BIAS, .., RES>
+    if (EPI != EPI_FULL && p.ep.ln_out != nullptr && p.out_mode == 0)
+      epilogue_layernorm(p, smem_u32(smem), m0 + quad * 32, quad, warp >> 2, lane);
     tc_fence_before();
     if (t == 0) TR(5);
   }
@@ -964,6 +1015,51 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __re
   epilogue_store4(ep, C, ldc, M, N, m, n, v);
 }
 
+// Split-K fold + bias + dropout + residual + LayerNorm for row-spanning outputs (N <= 128, N % 4 == 0): warp = row,
+// lane = one float4 of the row.  Replaces the fold and the stand-alone LayerNorm launch of the d <= 128 FFN's linear2.
+__global__ void __launch_bounds__(256) tc_splitk_reduce_ln_kernel(const float* __restrict__ partial, int splits, float* C,
+                                                                  int ldc, int M, int N, int Np, const Epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int n = 4 * lane;
+  const bool on = n < N;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (on) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      const float4 q = *reinterpret_cast<const float4*>(partial + ((size_t)z * M + m) * Np + n);
+      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[0] = s.x + b4.x; v[1] = s.y + b4.y; v[2] = s.z + b4.z; v[3] = s.w + b4.w;
+    if (ep.p_drop > 0.0f) {
+      float msk[4];
+      dropout_scale4(seed_value(ep.seed), ep.site, (uint64_t)m * (uint64_t)N + (uint64_t)n, ep.p_drop, 1.0f / (1.0f - ep.p_drop), msk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= msk[j];
+    }
+    if (ep.residual) {
+      const float4 r4 = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n);
+      v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+    }
+    *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  const float inv_n = 1.0f / (float)N;
+  const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * inv_n;
+  float sq = 0.f;
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] -= mean; sq += v[j] * v[j]; }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * inv_n + TC_LN_EPS);
+  if (on) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n)), e4 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n));
+    *reinterpret_cast<float4*>(ep.ln_out + (size_t)m * ldc + n) =
+        make_float4(v[0] * rstd * g4.x + e4.x, v[1] * rstd * g4.y + e4.y, v[2] * rstd * g4.z + e4.z, v[3] * rstd * g4.w + e4.w);
+  }
+}
+
 struct TcPlan { int splits; int kps; };
 
 // Split-K for an accumulating (red.global.add) product: no fold kernel, so the only costs are the per-CTA
@@ -1107,6 +1203,7 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.k_per_split = pa.kps; p.partial = nullptr; p.Np = Np; p.ep = ep;
     p.x1 = g_gemm_engine == GANFFN_GEMM_TF32X1;
+    p.ep.ln_out = nullptr;   // no LayerNorm behind an accumulating product
     p.out_mode = ((N & 3) == 0 && (ldc & 3) == 0 && al16(C)) ? 2 : 3;
     return launch_tc(p, transA, b_is_nk, EPI_PLAIN, dim3(cdiv(N, BN), cdiv(M, BM), pa.splits), st);
   }
@@ -1120,8 +1217,11 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     static const int astat_div = getenv("GANFFN_ASTAT_DIV") ? atoi(getenv("GANFFN_ASTAT_DIV")) : 1;   // tuning knob
     const int groups = std::max(1, std::min(ntiles, 148 / std::max(1, mtiles)) / std::max(1, astat_div));
     const int epi = pick_epilogue(ep, C, ldc, N);
-    return b_is_nk ? launch_astat2<true>(p, epi, dim3(groups, mtiles, 1), st)
-                   : launch_astat2<false>(p, epi, dim3(groups, mtiles, 1), st);
+    p.ep.ln_out = nullptr;   // N >= 256 here: the row spans several tiles
+    GANFFN_TRY(b_is_nk ? launch_astat2<true>(p, epi, dim3(groups, mtiles, 1), st)
+                       : launch_astat2<false>(p, epi, dim3(groups, mtiles, 1), st));
+    if (ep.ln_out) GANFFN_TRY(layernorm_fwd(C, ep.ln_gamma, ep.ln_beta, ep.ln_out, M, N, st));
+    return GANFFN_OK;
   }
   TcPlan pl = tc_plan(M, N, K);
   if (pl.splits > 1 && (scratch == nullptr || scratch_floats < (int64_t)pl.splits * M * Np)) {
@@ -1135,12 +1235,29 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
   p.out_mode = pl.splits > 1 ? 1 : 0;
   dim3 grid(cdiv(N, BN), cdiv(M, BM), pl.splits);
   const int epi = pl.splits > 1 ? EPI_PLAIN : pick_epilogue(ep, C, ldc, N);
+  // LayerNorm behind the product (Epilogue::ln_out): in the kernel's epilogue when one tile spans the row and the
+  // epilogue is the bias + [dropout] + residual specialisation, in the split-K fold when K was split, else stand-alone.
+  static const bool ln_fuse_off = getenv("GANFFN_NO_LN_FUSE") != nullptr;   // A/B switch
+  const bool ln = ep.ln_out != nullptr;
+  const bool ln_simple = ln && !ln_fuse_off && N <= BN && (N & 3) == 0 && ldc == N && ep.act == GANFFN_ACT_NONE &&
+                         ep.dact == DACT_NONE && !ep.pre && !ep.drop_before_act && ep.beta == 0.0f && ep.bias && ep.residual &&
+                         al16(ep.ln_gamma) && al16(ep.ln_beta) && al16(ep.ln_out) && al16(C) && al16(ep.bias) &&
+                         (ep.ldr & 3) == 0 && al16(ep.residual);
+  const bool ln_in_kernel = ln_simple && pl.splits == 1 && epi != EPI_FULL;
+  const bool ln_in_fold = ln_simple && pl.splits > 1;
+  if (!ln_in_kernel) p.ep.ln_out = nullptr;
   GANFFN_TRY(launch_tc(p, transA, b_is_nk, epi, grid, st));
   if (pl.splits > 1) {
-    const int64_t nvec = (int64_t)M * (Np / 4);
-    tc_splitk_reduce_kernel<<<cdiv(nvec, 256), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
-    GANFFN_LAUNCHED("tc_splitk_reduce_kernel");
+    if (ln_in_fold) {
+      tc_splitk_reduce_ln_kernel<<<cdiv(M, 8), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
+      GANFFN_LAUNCHED("tc_splitk_reduce_ln_kernel");
+    } else {
+      const int64_t nvec = (int64_t)M * (Np / 4);
+      tc_splitk_reduce_kernel<<<cdiv(nvec, 256), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
+      GANFFN_LAUNCHED("tc_splitk_reduce_kernel");
+    }
   }
+  if (ln && !ln_in_kernel && !ln_in_fold) GANFFN_TRY(layernorm_fwd(C, ep.ln_gamma, ep.ln_beta, ep.ln_out, M, N, st));
   return GANFFN_OK;
 }
 

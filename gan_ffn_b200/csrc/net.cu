@@ -223,9 +223,9 @@ int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const fl
     {
       Epilogue ep; ep.p_drop = p_enc; ep.seed = seed; ep.site = GANFFN_SITE_LAYER(l, 1);
       ep.residual = cur; ep.ldr = d;
+      ep.ln_gamma = P(lo[N1_W]); ep.ln_beta = P(lo[N1_B]); ep.ln_out = base + sl.x1;   // x1 = LN1(z1), fused where the engine can
       GANFFN_TRY(cx.linear_fwd(base + sl.o, P(lo[OUT_W]), P(lo[OUT_B]), base + sl.z1, T, d, d, ep));
     }
-    GANFFN_TRY(layernorm_fwd(base + sl.z1, P(lo[N1_W]), P(lo[N1_B]), base + sl.x1, T, d, st));
     {
       Epilogue ep; ep.act = GANFFN_ACT_RELU; ep.p_drop = p_enc; ep.seed = seed; ep.site = GANFFN_SITE_LAYER(l, 2);
       GANFFN_TRY(cx.linear_fwd(base + sl.x1, P(lo[L1_W]), P(lo[L1_B]), base + sl.h, T, nd.dff, d, ep));
@@ -233,9 +233,9 @@ int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const fl
     {
       Epilogue ep; ep.p_drop = p_enc; ep.seed = seed; ep.site = GANFFN_SITE_LAYER(l, 3);
       ep.residual = base + sl.x1; ep.ldr = d;
+      ep.ln_gamma = P(lo[N2_W]); ep.ln_beta = P(lo[N2_B]); ep.ln_out = base + sl.x2;   // x2 = LN2(z2)
       GANFFN_TRY(cx.linear_fwd(base + sl.h, P(lo[L2_W]), P(lo[L2_B]), base + sl.z2, T, d, nd.dff, ep));
     }
-    GANFFN_TRY(layernorm_fwd(base + sl.z2, P(lo[N2_W]), P(lo[N2_B]), base + sl.x2, T, d, st));
     cur = base + sl.x2;
   }
 
@@ -266,7 +266,11 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
             const float* d_out, const float* stash, float* grads, float* dx, float* scratch, int train, float p_head,
             Seed seed, int accumulate, cudaStream_t st) {
   GANFFN_TRY(net_check(nd));
-  GANFFN_CHECK_ARG(params && off && x && out && d_out && stash && grads && scratch, "net_bwd: null pointer");
+  GANFFN_CHECK_ARG(params && off && x && out && d_out && stash && scratch, "net_bwd: null pointer");
+  // grads == NULL: data gradient only (a frozen network, e.g. the discriminator inside train_gen whose parameter
+  // gradients the next train_disc zeroes before use, train_IEMOCAP.py:221): every weight / bias / LayerNorm gradient is skipped
+  const bool pg = grads != nullptr;
+  GANFFN_CHECK_ARG(pg || dx, "net_bwd: neither parameter gradients nor dx requested");
   const Stash sl = stash_layout(nd);
   const Scratch sc = scratch_layout(nd);
   const Ctx cx{nd, scratch + sc.gemm, sc.gemm_floats, scratch + sc.red, st};
@@ -274,10 +278,10 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
   const float p_pe = train ? P_PE : 0.f, p_enc = train ? P_ENC : 0.f, p_hd = train ? p_head : 0.f;
   const int64_t* hoff = off + (int64_t)nd.L * PER_LAYER;
   auto P = [&](int64_t o) { return params + o; };
-  auto G = [&](int64_t o) { return grads + o; };
+  auto G = [&](int64_t o) -> float* { return pg ? grads + o : nullptr; };
   const bool gen = nd.kind == GANFFN_NET_GENERATOR;
 
-  if (!accumulate) {
+  if (pg && !accumulate) {
     // every gradient below is accumulated (red.global.add from the GEMM / LayerNorm kernels): start from zero
     auto Z = [&](int64_t o, int64_t n) { if (o >= 0) cudaMemsetAsync(grads + o, 0, (size_t)n * sizeof(float), st); };
     for (int l = 0; l < nd.L; ++l) {
@@ -307,18 +311,18 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
   } else {
     // prob = sigmoid(drop(fc3(a2)))
     GANFFN_TRY(elementwise(d_out, out, hb3, (int64_t)T, EW_DSIGMOID_MASK, p_hd, seed, GANFFN_SITE_HEAD + 3, st));
-    GANFFN_TRY(cx.wgrad(hb3, stash + sl.a2, G(hoff[FC3_W]), G(hoff[FC3_B]), T, 1, nd.h2, accumulate));
+    if (pg) GANFFN_TRY(cx.wgrad(hb3, stash + sl.a2, G(hoff[FC3_W]), G(hoff[FC3_B]), T, 1, nd.h2, accumulate));
     Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = stash + sl.f2; ep.p_drop = p_hd; ep.seed = seed;
     ep.site = GANFFN_SITE_HEAD + 2;
     GANFFN_TRY(cx.dgrad(hb3, P(hoff[FC3_W]), hb2, T, 1, nd.h2, ep));
   }
-  GANFFN_TRY(cx.wgrad(hb2, stash + sl.a1, G(hoff[FC2_W]), G(hoff[FC2_B]), T, nd.h2, nd.h1, accumulate));
+  if (pg) GANFFN_TRY(cx.wgrad(hb2, stash + sl.a1, G(hoff[FC2_W]), G(hoff[FC2_B]), T, nd.h2, nd.h1, accumulate));
   {
     Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = stash + sl.f1; ep.p_drop = p_hd; ep.seed = seed;
     ep.site = GANFFN_SITE_HEAD + 1;
     GANFFN_TRY(cx.dgrad(hb2, P(hoff[FC2_W]), hb1, T, nd.h2, nd.h1, ep));
   }
-  GANFFN_TRY(cx.wgrad(hb1, stash + sl.g0, G(hoff[FC1_W]), G(hoff[FC1_B]), T, nd.h1, d, accumulate));
+  if (pg) GANFFN_TRY(cx.wgrad(hb1, stash + sl.g0, G(hoff[FC1_W]), G(hoff[FC1_B]), T, nd.h1, d, accumulate));
   {
     Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = last_x2; ep.p_drop = gen ? p_hd : 0.f; ep.seed = seed;
     ep.site = GANFFN_SITE_HEAD + 0;
@@ -328,12 +332,13 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
   // ---- encoder layers, last to first ----
   // Data gradients on the caller's stream, weight gradients on the side stream (see SideCtx).  wait_slot(k) orders a
   // kernel that overwrites the input of a still-pending weight-gradient product of slot k behind that product.
-  SideCtx* sx = side_ctx(st);
+  SideCtx* sx = pg ? side_ctx(st) : nullptr;
   float* gemm2 = scratch + sc.gemm2;
   float* dz1 = scratch + sc.dz1;
   float* dzd1_buf = scratch + sc.dzd1;
   if (sx) for (int i = 0; i < 4; ++i) sx->pending[i] = false;
   auto wgrad_side = [&](int slot, const float* dy, const float* xa, float* dw, float* dbias, int M, int N, int K) -> int {
+    if (!pg) return GANFFN_OK;
     if (!sx) return cx.wgrad(dy, xa, dw, dbias, M, N, K, accumulate);
     cudaEventRecord(sx->ready[slot], st);
     cudaStreamWaitEvent(sx->side, sx->ready[slot], 0);
@@ -404,7 +409,7 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
       GANFFN_TRY(elementwise(da, nullptr, db, (int64_t)T * d, EW_MASK, p_pe, seed, GANFFN_SITE_PE, st));
       dpe = db;
     }
-    GANFFN_TRY(cx.wgrad(dpe, x, G(hoff[OBJ_W]), G(hoff[OBJ_B]), T, d, nd.d_in, accumulate));
+    if (pg) GANFFN_TRY(cx.wgrad(dpe, x, G(hoff[OBJ_W]), G(hoff[OBJ_B]), T, d, nd.d_in, accumulate));
     if (dx) GANFFN_TRY(cx.dgrad(dpe, P(hoff[OBJ_W]), dx, T, d, nd.d_in, Epilogue{}));
   } else if (dx) {
     GANFFN_TRY(elementwise(da, nullptr, dx, (int64_t)T * d, EW_MASK, p_pe, seed, GANFFN_SITE_PE, st));

@@ -291,6 +291,8 @@ class ParamArena:
         # that completes the expected count launches the per-layer all-reduces (overlapped with the rest of that
         # pass) and leaves their handles in ``reduce_works`` for FusedAdam.step() to wait on
         self.reduce_hook, self.reduce_works = None, None
+        # parameter gradients switched off for the calls made inside ``frozen_parameters(module)``
+        self.frozen = False
 
     def prezero(self) -> None:
         """zero_grad(set_to_none=True) for an arena: the ``.grad`` views are dropped by the caller; the buffer is
@@ -333,8 +335,10 @@ class _NetFunction(torch.autograd.Function):
     only autograd edge is the input ``x``."""
 
     @staticmethod
-    def forward(ctx, x, anchor, arena: ParamArena, spec: NetSpec, pe, train: bool, p_head: float, seed: int, seed_ptr):
+    def forward(ctx, x, anchor, arena: ParamArena, spec: NetSpec, pe, train: bool, p_head: float, seed: int, seed_ptr,
+                param_grads: bool = True):
         L = lib()
+        ctx.param_grads = param_grads
         S, B, d_in = x.shape
         dims = spec.dims(S, B, d_in)
         stash_n = L.query("ganffn_net_stash_floats", *dims)
@@ -362,6 +366,14 @@ class _NetFunction(torch.autograd.Function):
         cur = torch.cuda.current_stream(x.device)
         if _lanes.streams and _lanes.is_lane(cur.cuda_stream):
             _lanes.touch(cur)   # a backward pass on a lane (autograd runs it where the forward ran): join before use
+        if not ctx.param_grads:
+            # frozen network (frozen_parameters): data gradient only, the gradient arena is not touched
+            if dx is not None:
+                _call(x, "ganffn_net_bwd", spec.kind, ptr(arena.flat), arena.table.ctypes.data, ptr(x), ptr(out), ptr(d_out),
+                      ptr(ctx.stash), None, ptr(dx), ptr(ws), S, B, d_in, spec.d, spec.nhead, spec.dff,
+                      spec.nlayers, spec.h1, spec.h2, int(ctx.train), float(ctx.p_head), ctx.seed, ctx.seed_ptr, 1, _stream(x))
+            ctx.stash = None
+            return dx, None, None, None, None, None, None, None, None, None
         if not arena.grads_live():
             # Parameter gradients are accumulated by the kernels (red.global.add from the wgrad GEMMs and the
             # LayerNorm backward), torch-style: a fresh backward starts from a zeroed arena (one memset) -- done
@@ -385,7 +397,28 @@ class _NetFunction(torch.autograd.Function):
             if hook["seen"] == hook["expected"]:
                 arena.reduce_works = hook["reducer"].reduce_arena_by_layer(arena, spec.nlayers, cur)
                 arena.reduce_hook = None
-        return dx, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None
+
+
+class frozen_parameters:
+    """``with frozen_parameters(net): y = net(x)`` -- calls of ``net`` made inside the block back-propagate to their
+    input only; no weight, bias or LayerNorm gradient of ``net`` is computed or accumulated (the usual ``requires_grad_
+    (False)`` freeze of a discriminator while its generator trains, without touching a hundred parameter flags per
+    sub-step).  The reference's ``train_gen`` (train_IEMOCAP.py:230-252) does compute the discriminator's parameter
+    gradients, but nothing ever reads them: only the generator's optimizer steps, and the discriminator's next use is
+    ``train_disc``, which starts with ``opt.zero_grad()`` (:221)."""
+
+    def __init__(self, net):
+        self.arena = net.arena()
+
+    def __enter__(self):
+        self.prev = self.arena.frozen
+        self.arena.frozen = True
+        return self
+
+    def __exit__(self, *exc):
+        self.arena.frozen = self.prev
+        return False
 
 
 def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Tensor, train: bool, p_head: float):
@@ -400,10 +433,11 @@ def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Ten
         else:
             seed = next_seed()
     anchor = arena.flat
-    if arena.requires_grad and torch.is_grad_enabled():
+    param_grads = arena.requires_grad and not arena.frozen
+    if param_grads and torch.is_grad_enabled():
         anchor = arena.flat.detach().requires_grad_(True)  # makes autograd call backward even for data inputs
     if not _lanes.active:
-        return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr)
+        return _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr, param_grads)
     main = torch.cuda.current_stream(x.device)
     k, lane = _lanes.lane(x.device)
     lane.wait_stream(main)                                   # fork
@@ -412,7 +446,7 @@ def net_forward(x: torch.Tensor, arena: ParamArena, spec: NetSpec, pe: torch.Ten
         lane.wait_event(src[0])                              # input made by another network still on its lane
     x.record_stream(lane)
     with torch.cuda.stream(lane):
-        out = _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr)
+        out = _NetFunction.apply(x, anchor, arena, spec, pe, train, p_head, seed, seed_ptr, param_grads)
         ev = torch.cuda.Event()
         ev.record(lane)
     out.record_stream(main)

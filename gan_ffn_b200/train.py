@@ -79,13 +79,32 @@ def train_gen(gen, real_gen, disc, opt, adversarial_loss, valid, fake):
     return res
 
 
+def train_gen_frozen_disc(gen, real_gen, disc, opt, adversarial_loss, valid, fake):
+    """``train_gen`` with the discriminator frozen for the sub-step: the generator's loss, gradients and update are
+    those of reference train_IEMOCAP.py:230-252; the discriminator's weight gradients -- which the reference computes
+    and never uses (its next use, ``train_disc``, starts with ``opt.zero_grad()``, :221) -- are not computed
+    (a quarter of the backward GEMM work of the stage-1 batch)."""
+    gen.train()
+    disc.eval()
+
+    opt.zero_grad()
+    fusion = gen(real_gen)
+    with GF.frozen_parameters(disc):
+        prob = disc(fusion)
+    g_loss = adversarial_loss(prob, valid)
+    res = g_loss.detach()
+    g_loss.backward()
+    opt.step()
+    return res
+
+
 class GANTrainer:
     """Stage 1 (reference ``train_GAN``, train_IEMOCAP.py:255-393): six networks, six Adam
     optimizers (generators lr, discriminators lr/2, text generator lr*1.1), BCE adversarial loss."""
 
     def __init__(self, acoustic_gen, visual_gen, text_gen, acoustic_disc, visual_disc, text_disc, lr=GAN_LR, b1=GAN_B1,
                  b2=GAN_B2, grad_reducer=None, world_size: int = 1, overlap: bool = True, batch_disc: bool = True,
-                 chains: int = 2):
+                 chains: int = 2, freeze_disc: bool = True):
         self.nets = dict(acoustic_gen=acoustic_gen, visual_gen=visual_gen, text_gen=text_gen, acoustic_disc=acoustic_disc,
                          visual_disc=visual_disc, text_disc=text_disc)
         mk = lambda net, rate: FusedAdam(net, lr=rate, betas=(b1, b2), grad_reducer=grad_reducer)
@@ -101,6 +120,8 @@ class GANTrainer:
         self.overlap = overlap
         # train_disc as one discriminator pass over [real | fake] (train_disc_batched) instead of two
         self.batch_disc = batch_disc
+        # train_gen without the discriminator's never-read weight gradients (train_gen_frozen_disc); False = reference body
+        self.freeze_disc = freeze_disc
         # independent sub-steps on concurrent chains (see _batch); 1 = the reference's strictly serial order
         self.chains = chains
         self._chain_streams = {}
@@ -149,7 +170,8 @@ class GANTrainer:
         def run(kind, d, g):
             if kind == "D":
                 return disc_step(n[d], real[d], n[g], real[g], opts[d], adv, valid, fake)
-            return train_gen(n[g], real[g], n[d], opts[g], adv, valid, fake)
+            gen_step = train_gen_frozen_disc if self.freeze_disc else train_gen
+            return gen_step(n[g], real[g], n[d], opts[g], adv, valid, fake)
 
         loss = {}
         chains = self.chains if (self.overlap and not GF._deterministic["on"]) else 1

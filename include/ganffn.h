@@ -103,6 +103,15 @@ int ganffn_linear_fwd(const float* x, const float* w, const float* bias, const f
                       float* y, float* pre, int M, int N, int K, int act, int drop_before_act,
                       float p_drop, uint64_t seed, int site, float* scratch,
                       int64_t scratch_floats, void* stream);
+/* Post-norm sublayer tail in one call: z[M,N] = residual + drop(x[M,K] @ w[N,K]^T + bias), y[M,N] = LayerNorm(z) * gamma
+ * + beta (eps 1e-5).  Replaces `x = norm(x + dropout(linear(..)))` of TransformerEncoderLayer (torch transformer.py
+ * :944-982, post-norm branch; out-proj + norm1 and linear2 + norm2).  z is kept because the backward pass reads it.
+ * The tcgen05 engine normalises inside the GEMM epilogue when N <= 128 (or inside its split-K fold); other shapes and
+ * the FFMA engine run the stand-alone LayerNorm kernel behind the product -- same results either way. */
+int ganffn_linear_ln_fwd(const float* x, const float* w, const float* bias, const float* residual,
+                         const float* gamma, const float* beta, float* z, float* y, int M, int N, int K,
+                         float p_drop, uint64_t seed, int site, float* scratch, int64_t scratch_floats,
+                         void* stream);
 /* Split-K workspace (floats) the GEMM engines want for an [M,N,K] product; may be 0. */
 int64_t ganffn_gemm_scratch_floats(int M, int N, int K);
 
@@ -217,7 +226,9 @@ int ganffn_net_fwd(int kind, const float* params, const int64_t* off, const floa
                    int d, int nhead, int dff, int nlayers, int h1, int h2, int train, float p_head,
                    uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* Backward of the above.  grads has the arena's layout; accumulate != 0 adds into it.
- * dx may be NULL when the input needs no gradient.  scratch: ganffn_net_scratch_floats(). */
+ * dx may be NULL when the input needs no gradient.  grads may be NULL for a frozen network (data gradient only:
+ * no weight, bias or LayerNorm gradient is computed -- the discriminator inside train_gen, whose parameter gradients
+ * the next train_disc zeroes before use, train_IEMOCAP.py:221, 245-251).  scratch: ganffn_net_scratch_floats(). */
 int ganffn_net_bwd(int kind, const float* params, const int64_t* off, const float* x,
                    const float* out, const float* d_out_grad, const float* stash, float* grads,
                    float* dx, float* scratch, int S, int B, int d_in, int d, int nhead, int dff,

@@ -102,6 +102,33 @@ def test_linear_fwd_epilogues_with_dropout_and_residual(L, engine, act, dba):
     close(y, ref, "epilogue output", floor=2e-6)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("M,N,K,p", [(3008, 100, 100, 0.1), (3008, 100, 100, 0.0), (3008, 100, 2048, 0.1), (6016, 100, 2048, 0.0),
+                                     (130, 128, 260, 0.1), (97, 64, 100, 0.0), (300, 512, 512, 0.1), (3008, 512, 2048, 0.0),
+                                     (50, 100, 36, 0.1), (282, 36, 100, 0.1)])
+def test_linear_layernorm_tail(L, engine, M, N, K, p):
+    """z = residual + drop(linear(x)), y = LayerNorm(z): fused in the tcgen05 epilogue / split-K fold for N <= 128,
+    stand-alone LayerNorm elsewhere (torch transformer.py:944-982, post-norm)."""
+    L.cdll.ganffn_set_gemm_engine(engine)
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K)
+    x, w, b, r = (torch.randn(*s, generator=g) for s in ((M, K), (N, K), (N,), (M, N)))
+    w = w / math.sqrt(K)
+    gamma, beta = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    xd, wd, bd, rd, gd, btd = (dev(t) for t in (x, w, b, r, gamma, beta))
+    z = torch.empty(M, N, device="cuda")
+    y = torch.empty(M, N, device="cuda")
+    seed, site = 0xABCDEF0123, 33
+    ws, n = gemm_ws(L, M, N, K)
+    L.call("ganffn_linear_ln_fwd", P(xd), P(wd), P(bd), P(rd), P(gd), P(btd), P(z), P(y), M, N, K, p, seed, site, P(ws), n,
+           stream())
+    from gan_ffn_b200.functional import dropout_mask
+    mask = dropout_mask(M, N, p, seed, site).double().cpu()
+    zr = (x.double() @ w.double().T + b.double()) * mask + r.double()
+    yr = torch.nn.functional.layer_norm(zr, (N,), gamma.double(), beta.double(), 1e-5)
+    close(z, zr, f"pre-norm sum {M}x{N}x{K}", floor=2e-6)
+    close(y, yr, f"LayerNorm output {M}x{N}x{K}", floor=2e-6)
+
+
 def test_dropout_mask_statistics_and_determinism(L):
     from gan_ffn_b200.functional import dropout_mask
     for p in (0.1, 0.2, 0.6):

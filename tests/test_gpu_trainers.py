@@ -87,15 +87,19 @@ def _compare_updates(name, ours_before, ours_after, port_before, port_after, lr,
     assert stats["max_err_over_lr"] <= steps * 2.0 * 1.001, stats
 
 
+@pytest.mark.parametrize("freeze_disc", [False, True], ids=["reference-train_gen", "frozen-disc"])
 @pytest.mark.parametrize("batch_disc", [False, True], ids=["two-pass-disc", "batched-disc"])
 @pytest.mark.parametrize("overlap", [False, True], ids=["serial", "lanes+chains"])
-def test_gan_batch_and_classifier_step_match_reference_port(overlap, batch_disc):
+def test_gan_batch_and_classifier_step_match_reference_port(overlap, batch_disc, freeze_disc):
     """batch_disc=False is the reference's train_disc body verbatim (two discriminator passes); True runs them as one
-    pass over [real | fake] (train.train_disc_batched) -- both must match the port."""
+    pass over [real | fake] (train.train_disc_batched) -- both must match the port.  freeze_disc=False is the
+    reference's train_gen body verbatim; True skips the discriminator weight gradients that train_gen computes and
+    nothing reads (train.train_gen_frozen_disc) -- losses and every network's update must not change."""
     from gan_ffn_b200 import synthetic
     nets, ffn, gan, cls, pnets, pffn, port = _build_pair()
     gan.overlap = cls.overlap = overlap
     gan.batch_disc = batch_disc
+    gan.freeze_disc = freeze_disc
     batch = synthetic.make_batch(n_dialogues=4, lengths=[14, 9, 12, 5], seed=11)
     cb = batch.to("cuda")
 
@@ -135,6 +139,35 @@ def test_gan_batch_and_classifier_step_match_reference_port(overlap, batch_disc)
     l_eval, _, _ = cls.step(cb, train=False)
     l_eval_ref, _ = port.classifier_step(batch, train=False)
     assert abs(float(l_eval) - float(l_eval_ref)) <= 5 * H.RTOL * abs(float(l_eval_ref))
+
+
+def test_frozen_parameters_gives_the_same_input_gradient_and_leaves_the_arena_alone():
+    """``frozen_parameters(net)``: ganffn_net_bwd with grads = NULL -- dx identical to the full backward pass, no
+    parameter gradient written."""
+    import gan_ffn_b200 as GB
+    from gan_ffn_b200 import functional as GF
+    torch.manual_seed(5)
+    for net, width in ((GB.TextDiscriminator(100), 100), (GB.VisualDiscriminator(100), 512), (GB.AcousticGenerator(100), 100)):
+        net = net.cuda().train()
+        GB.manual_seed(123)
+        x1 = torch.randn(21, 3, width, device="cuda", requires_grad=True)
+        y1 = net(x1)
+        g = torch.randn_like(y1)
+        y1.backward(g)
+        ref_dx = x1.grad.detach().clone()
+        assert float(net.arena().grad.abs().sum()) > 0
+        net.arena().grad.zero_()
+        GB.manual_seed(123)                      # the same dropout masks
+        x2 = x1.detach().clone().requires_grad_(True)
+        with GF.frozen_parameters(net):
+            y2 = net(x2)
+        assert torch.equal(y1.detach(), y2.detach())
+        y2.backward(g)
+        assert torch.equal(x2.grad, ref_dx), "data gradient must not depend on whether parameter gradients are computed"
+        assert float(net.arena().grad.abs().sum()) == 0.0, "a frozen network's gradient arena must stay untouched"
+        x3 = torch.randn(21, 3, width, device="cuda")     # nothing requires grad: backward is never called
+        with GF.frozen_parameters(net):
+            assert not net(x3).requires_grad
 
 
 def test_gan_batch_graph_replay_matches_reference_port():
