@@ -15,6 +15,13 @@ namespace ganffn {
 namespace {
 
 constexpr int NG = 4;                                // warp groups
+// resident CTAs per SM the small-head kernels are compiled for (register cap 65536 / (128 * n)); build-time tuning knobs
+#ifndef GANFFN_ATT_FWD_MINB
+#define GANFFN_ATT_FWD_MINB 5
+#endif
+#ifndef GANFFN_ATT_BWD_MINB
+#define GANFFN_ATT_BWD_MINB 5
+#endif
 constexpr int MAX_RW = (GANFFN_MAX_SEQ + 31) / 32;   // row warps per group
 constexpr int KPG = ((GANFFN_MAX_SEQ + 4 * NG - 1) / (4 * NG)) * 4;   // max keys per group (multiple of 4)
 
@@ -61,24 +68,33 @@ __device__ __forceinline__ void row_to_regs(const float* __restrict__ s, float* 
   }
 }
 
+// Packed fp32 FMA (sm_100 FFMA2: two fused multiply-adds per instruction).  These kernels are bound by instruction
+// issue, not by the FMA pipe (r2 ncu: fma pipe 15 % busy, issue slots 37 % with every warp waiting on its own
+// dependent chain), so halving the FMA instruction count is worth more than any reordering.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 // q (registers) . row (warp-uniform smem address)
 template <int HD>
 __device__ __forceinline__ float dot_smem(const float* q, const float* __restrict__ krow) {
   float s = 0.f;
   constexpr int W = Cfg<HD>::W;
   if (W == 4) {
+    float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < HD / 4; ++c) {
       float4 k = *reinterpret_cast<const float4*>(krow + 4 * c);
-      s = fmaf(q[4 * c], k.x, s); s = fmaf(q[4 * c + 1], k.y, s);
-      s = fmaf(q[4 * c + 2], k.z, s); s = fmaf(q[4 * c + 3], k.w, s);
+      s2 = ffma2(make_float2(q[4 * c], q[4 * c + 1]), make_float2(k.x, k.y), s2);
+      s2 = ffma2(make_float2(q[4 * c + 2], q[4 * c + 3]), make_float2(k.z, k.w), s2);
     }
+    s = s2.x + s2.y;
   } else if (W == 2) {
+    float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < HD / 2; ++c) {
       float2 k = *reinterpret_cast<const float2*>(krow + 2 * c);
-      s = fmaf(q[2 * c], k.x, s); s = fmaf(q[2 * c + 1], k.y, s);
+      s2 = ffma2(make_float2(q[2 * c], q[2 * c + 1]), k, s2);
     }
+    s = s2.x + s2.y;
   } else {
 #pragma unroll
     for (int c = 0; c < HD; ++c) s = fmaf(q[c], krow[c], s);
@@ -326,18 +342,21 @@ __global__ void __launch_bounds__(NG * MAX_RW * 32) attention_bwd_kernel(
 template <int HD>
 __device__ __forceinline__ void axpy_row(float a, const float* __restrict__ row, float* acc) {
   constexpr int W = Cfg<HD>::W;
+  const float2 a2 = make_float2(a, a);
   if (W == 4) {
 #pragma unroll
     for (int c = 0; c < HD / 4; ++c) {
       const float4 v = *reinterpret_cast<const float4*>(row + 4 * c);
-      acc[4 * c] = fmaf(a, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(a, v.y, acc[4 * c + 1]);
-      acc[4 * c + 2] = fmaf(a, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(a, v.w, acc[4 * c + 3]);
+      const float2 r0 = ffma2(a2, make_float2(v.x, v.y), make_float2(acc[4 * c], acc[4 * c + 1]));
+      const float2 r1 = ffma2(a2, make_float2(v.z, v.w), make_float2(acc[4 * c + 2], acc[4 * c + 3]));
+      acc[4 * c] = r0.x; acc[4 * c + 1] = r0.y; acc[4 * c + 2] = r1.x; acc[4 * c + 3] = r1.y;
     }
   } else if (W == 2) {
 #pragma unroll
     for (int c = 0; c < HD / 2; ++c) {
       const float2 v = *reinterpret_cast<const float2*>(row + 2 * c);
-      acc[2 * c] = fmaf(a, v.x, acc[2 * c]); acc[2 * c + 1] = fmaf(a, v.y, acc[2 * c + 1]);
+      const float2 r = ffma2(a2, v, make_float2(acc[2 * c], acc[2 * c + 1]));
+      acc[2 * c] = r.x; acc[2 * c + 1] = r.y;
     }
   } else {
 #pragma unroll
@@ -376,7 +395,7 @@ __device__ __forceinline__ float dot_regs(const float* a, const float* b) {
 // slots (the second with 24 CTAs): 24.7 / 37.4 us for 5.9 / 12 us of issue time.  With 32-row CTAs of 128 threads
 // (7.5 - 16 KB of shared memory) 960 CTAs are all resident at once and nothing is quantised.
 template <int HD>
-__global__ void __launch_bounds__(NG * 32, 5) attention_fwd_small_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(NG * 32, GANFFN_ATT_FWD_MINB) attention_fwd_small_kernel(const float* __restrict__ qkv,
                                                                         float* __restrict__ o, float* __restrict__ lse,
                                                                         int S, int B, int d, int nhead, float p_drop,
                                                                         const Seed seed_ref, uint32_t site) {
@@ -474,7 +493,7 @@ __global__ void __launch_bounds__(NG * 32, 5) attention_fwd_small_kernel(const f
 // sweep B: one 64-bit word covers four consecutive keys of one query, i.e. four neighbouring lanes; for a chunk of four
 // queries each lane generates the word of query (lane & 3) of its key quad and the quad exchanges them by shuffle.
 template <int HD>
-__global__ void __launch_bounds__(NG * 32, 5) attention_bwd_small_kernel(
+__global__ void __launch_bounds__(NG * 32, GANFFN_ATT_BWD_MINB) attention_bwd_small_kernel(
     const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
     const float* __restrict__ d_o, float* __restrict__ dqkv, int S, int B, int d, int nhead, float p_drop,
     const Seed seed_ref, uint32_t site) {

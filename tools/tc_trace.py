@@ -14,6 +14,7 @@ dev = "cuda"
 st = torch.cuda.current_stream().cuda_stream
 import os
 L.cdll.ganffn_debug_tc_flags(int(os.environ.get("TCDBG", "0")))
+KIND = os.environ.get("TCKIND", "fwd")      # fwd: y = x w^T (K-major A);  wgrad: dw = dy^T x (MN-major A, red.global.add epilogue)
 args = [int(a) for a in sys.argv[1:]]
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 for i in range(0, len(args), 3):
@@ -26,8 +27,14 @@ for i in range(0, len(args), 3):
             flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        L.call("ganffn_linear_fwd", x.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), None, M, N, K, 0, 0, 0.0, 0, 0,
-               ws.data_ptr(), ws.numel(), st)
+        if KIND == "wgrad":   # here (M, N, K) are the linear layer's: the product is [N x K] over M rows
+            if rep == 0:
+                dyw, dw = torch.randn(M, N, device=dev), torch.zeros(N, K, device=dev)
+                ws2 = torch.empty(max(int(L.cdll.ganffn_wgrad_scratch_floats(M, N, K)), 1), device=dev)
+            L.call("ganffn_linear_wgrad", dyw.data_ptr(), x.data_ptr(), dw.data_ptr(), None, M, N, K, 1, ws2.data_ptr(), st)
+        else:
+            L.call("ganffn_linear_fwd", x.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), None, M, N, K, 0, 0, 0.0, 0, 0,
+                   ws.data_ptr(), ws.numel(), st)
         b.record()
         torch.cuda.synchronize()
         buf = (ctypes.c_longlong * 128)()
