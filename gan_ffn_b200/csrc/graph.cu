@@ -264,6 +264,23 @@ __global__ void __launch_bounds__(256) graph_unpack_kernel(const float* __restri
   reinterpret_cast<float4*>(out)[idx] = v;
 }
 
+// Device-side collate of the loader's per-utterance metadata (reference dataloader.py:44-58: speaker one-hots, the
+// all-ones utterance mask and the labels of each dialogue, zero-padded by pad_sequence): thread = one padded slot.
+__global__ void __launch_bounds__(256) collate_meta_kernel(const int* __restrict__ speakers, const int64_t* __restrict__ labels,
+                                                           const int* __restrict__ lengths, const int64_t* __restrict__ node_off,
+                                                           float* __restrict__ qmask, float* __restrict__ umask,
+                                                           int64_t* __restrict__ label, int S, int B, int n_spk) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)S * B) return;
+  const int b = (int)(idx % B), t = (int)(idx / B);          // qmask is (S,B,n_spk): consecutive threads write consecutive rows
+  const bool real = t < lengths[b];
+  const int64_t n = node_off[b] + t;
+  const int sp = real ? speakers[n] : -1;
+  for (int k = 0; k < n_spk; ++k) qmask[idx * n_spk + k] = sp == k ? 1.f : 0.f;
+  umask[(int64_t)b * S + t] = real ? 1.f : 0.f;              // (B,S)
+  label[(int64_t)b * S + t] = real ? labels[n] : 0;
+}
+
 constexpr int GV = 4;   // float4 per lane at most: d <= 512 (the kernels are instantiated for 1 and GV)
 
 __device__ __forceinline__ void add4(float4& a, const float4 v, float w) {
@@ -642,6 +659,15 @@ int graph_unpack(const float* x_nodes, const int* lengths, const int64_t* node_o
   return GANFFN_OK;
 }
 
+int collate_meta(const int* speakers, const int64_t* labels, const int* lengths, const int64_t* node_off, float* qmask,
+                 float* umask, int64_t* label, int S, int B, int n_spk, cudaStream_t st) {
+  GANFFN_CHECK_ARG(speakers && labels && lengths && node_off && qmask && umask && label, "collate_meta: null pointer");
+  GANFFN_CHECK_ARG(S >= 1 && B >= 1 && n_spk >= 1, "collate_meta: S=%d B=%d n_speakers=%d", S, B, n_spk);
+  collate_meta_kernel<<<cdiv((int64_t)S * B, 256), 256, 0, st>>>(speakers, labels, lengths, node_off, qmask, umask, label, S, B, n_spk);
+  GANFFN_LAUNCHED("collate_meta_kernel");
+  return GANFFN_OK;
+}
+
 int graph_gather_typed(const float* x, const int64_t* rowptr, const int* col, const int* etype, const float* inv_cnt,
                        float* out, int64_t N, int R, int d, const int64_t* node_off, int B, int max_len, cudaStream_t st) {
   GANFFN_CHECK_ARG(x && rowptr && col && etype && inv_cnt && out, "graph_gather_typed: null pointer");
@@ -724,6 +750,11 @@ int ganffn_graph_pack(const float* x_sbd, const int* node_b, const int* node_t, 
 int ganffn_graph_unpack(const float* x_nodes, const int* lengths, const int64_t* node_off, float* x_sbd, int S, int B, int d,
                         void* stream) {
   return graph_unpack(x_nodes, lengths, node_off, x_sbd, S, B, d, GS(stream));
+}
+
+int ganffn_collate_meta(const int* speakers, const int64_t* labels, const int* lengths, const int64_t* node_off, float* qmask,
+                        float* umask, int64_t* label, int S, int B, int n_speakers, void* stream) {
+  return collate_meta(speakers, labels, lengths, node_off, qmask, umask, label, S, B, n_speakers, GS(stream));
 }
 
 int ganffn_graph_gather_typed(const float* x, const int64_t* rowptr, const int* col, const int* etype, const float* inv_cnt,

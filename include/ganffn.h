@@ -275,6 +275,13 @@ int ganffn_graph_pack(const float* x_sbd, const int* node_b, const int* node_t, 
                       int64_t n_nodes, int B, int d, void* stream);
 int ganffn_graph_unpack(const float* x_nodes, const int* lengths, const int64_t* node_off, float* x_sbd,
                         int S, int B, int d, void* stream);
+/* Device-side collate (reference dataloader.py:55-58, `pad_sequence` inside collate_fn).  The loader's batch is copied
+ * to the device PACKED -- features [N, d] of the real utterances only, speakers [N], labels [N], lengths [B],
+ * node_off [B+1] = exclusive prefix sums of lengths -- and padded here: features with ganffn_graph_unpack (packed
+ * [N, d] -> zero-padded (S,B,d)), the per-utterance metadata with this call:
+ *   qmask (S,B,n_speakers) one-hot speakers, umask (B,S) 1/0, label (B,S) int64, all zero at padded slots. */
+int ganffn_collate_meta(const int* speakers, const int64_t* labels, const int* lengths, const int64_t* node_off,
+                        float* qmask, float* umask, int64_t* label, int S, int B, int n_speakers, void* stream);
 /* Relation-typed mean aggregation: out[n, r, :] = inv_cnt[n, r] * sum_{e in row n, etype[e] = r} x[col[e], :].
  * out is [N, n_rel, d] (empty relations are written as zeros): the dense contraction with the relation weights is
  * then one GEMM of [N, n_rel*d] x [n_rel*d, h] (ganffn_linear_fwd).
