@@ -293,10 +293,21 @@ class ParamArena:
         self.reduce_hook, self.reduce_works = None, None
         # parameter gradients switched off for the calls made inside ``frozen_parameters(module)``
         self.frozen = False
+        # data parallel: FusedAdam may run this arena's update on the communication stream, behind its gradient
+        # all-reduce (``defer_step``); ``update_event`` then marks the update, and every later reader / writer of the
+        # arena (forward passes, zero_grad) waits for it on its own stream (``wait_updated``)
+        self.update_event = None
+
+    def wait_updated(self, stream=None) -> None:
+        """Orders ``stream`` (default: the current one) behind a deferred optimizer update of this arena."""
+        ev = self.update_event
+        if ev is not None:
+            (stream or torch.cuda.current_stream(self.flat.device)).wait_event(ev)
 
     def prezero(self) -> None:
         """zero_grad(set_to_none=True) for an arena: the ``.grad`` views are dropped by the caller; the buffer is
         cleared now, on the caller's stream, so that backward passes on several lanes can accumulate into it."""
+        self.wait_updated()          # a deferred Adam step may still be reading the gradients
         self.grad.zero_()
         self.prezeroed = True
         self.zero_event, self.zero_stream = None, None
@@ -339,6 +350,7 @@ class _NetFunction(torch.autograd.Function):
                 param_grads: bool = True):
         L = lib()
         ctx.param_grads = param_grads
+        arena.wait_updated()         # deferred optimizer step on the communication stream (data parallel)
         S, B, d_in = x.shape
         dims = spec.dims(S, B, d_in)
         stash_n = L.query("ganffn_net_stash_floats", *dims)
@@ -395,7 +407,11 @@ class _NetFunction(torch.autograd.Function):
         if hook is not None:
             hook["seen"] += 1
             if hook["seen"] == hook["expected"]:
-                arena.reduce_works = hook["reducer"].reduce_arena_by_layer(arena, spec.nlayers, cur)
+                red = hook["reducer"]
+                # large arenas: per-encoder-layer buckets overlapped with the rest of this pass; small ones: one
+                # all-reduce as soon as the pass is complete (it then overlaps whatever else the step is doing)
+                arena.reduce_works = (red.reduce_arena_by_layer(arena, spec.nlayers, cur)
+                                      if arena.numel >= getattr(red, "overlap_min_numel", 0) else red.reduce_arena_whole(arena, cur))
                 arena.reduce_hook = None
         return dx, None, None, None, None, None, None, None, None, None
 
@@ -467,6 +483,7 @@ class _ArenaLinearFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, arena: ParamArena, ow: int, ob: int, n_out: int):
         L = lib()
+        arena.wait_updated()
         S, B, K = x.shape
         M = S * B
         y = torch.empty((S, B, n_out), dtype=torch.float32, device=x.device)

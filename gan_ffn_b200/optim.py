@@ -42,6 +42,10 @@ class FusedAdam:
         # and the `object` projection of the batched visual discriminator are); concurrent passes on different lanes
         # (the two-pass train_disc body) fall back to one all-reduce per arena at step()
         self.sequential_backwards = False
+        # data parallel: run the arena updates on the communication stream, behind their all-reduces, instead of making
+        # the caller's stream wait for the collectives; the arenas' later users wait for ``update_event`` (functional.
+        # ParamArena.wait_updated).  Set by the trainers of train.py, which join the events at the end of a batch.
+        self.defer_step = False
         self.grad_scale = 1.0
         self.state = {}                           # id(arena or param) -> dict(step, m, v)
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
@@ -84,7 +88,6 @@ class FusedAdam:
                 # the all-reduce itself, layer by layer (functional._NetFunction.backward -> GradReducer.reduce_arena_by_layer)
                 ar.reduce_hook = ({"reducer": self.grad_reducer, "expected": int(self.expected_backwards), "seen": 0}
                                   if (self.grad_reducer is not None and self.overlap_reduce and ar.grad.is_cuda and
-                                      ar.numel >= getattr(self.grad_reducer, "overlap_min_numel", 0) and
                                       (self.expected_backwards == 1 or self.sequential_backwards)) else None)
 
     def _state_for(self, key, like: torch.Tensor):
@@ -109,7 +112,31 @@ class FusedAdam:
         arenas = self._arenas()
         live = [ar for ar in arenas if ar.grads_live()]
         loose = [p for p in self._loose(arenas) if p.grad is not None]
-        if self.grad_reducer is not None:
+        deferred = (self.grad_reducer is not None and self.defer_step and bool(live) and live[0].flat.is_cuda)
+        if deferred:
+            # Collectives and arena updates on the communication stream: the caller's stream goes straight on to the next
+            # sub-step (whose first network usually is a different one) while this network's gradients are summed and
+            # its Adam step runs; its next forward pass / zero_grad waits for ``update_event``.
+            cur = torch.cuda.current_stream(live[0].flat.device)
+            self.grad_reducer.reduce([p.grad for p in loose])        # a few hundred floats: stays on the caller's stream
+            comm = None
+            for ar in live:
+                ar.reduce_hook = None
+                if ar.reduce_works is None:
+                    ar.reduce_works = self.grad_reducer.reduce_arena_whole(ar, cur)
+                works, comm = ar.reduce_works
+                ar.reduce_works = None
+                with torch.cuda.stream(comm):
+                    for w in works:
+                        w.wait()
+                    st = self._state_for(ar, ar.flat)
+                    GF._call(ar.flat, "ganffn_adam_step_dev", ptr(ar.flat), ptr(ar.grad), ptr(st["m"]), ptr(st["v"]), ar.numel,
+                             ptr(st["step_t"]), lr, b1, b2, self.eps, self.weight_decay, self.grad_scale, comm.cuda_stream)
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                ar.update_event = ev
+            live = []
+        elif self.grad_reducer is not None:
             cur = torch.cuda.current_stream() if torch.cuda.is_available() else None
             late = [ar for ar in live if ar.reduce_works is None]
             self.grad_reducer.reduce([ar.grad for ar in late] + [p.grad for p in loose])
@@ -130,3 +157,14 @@ class FusedAdam:
             g = p.grad.contiguous()
             GF._call(p, "ganffn_adam_step_dev", ptr(p), ptr(g), ptr(st["m"]), ptr(st["v"]), p.numel(), ptr(st["step_t"]), lr,
                    b1, b2, self.eps, self.weight_decay, self.grad_scale, GF._stream(p))
+
+    def join_deferred(self, stream=None) -> None:
+        """Orders ``stream`` (default: the current one) behind every deferred arena update of this optimizer and clears the
+        marks (end of a train step: a captured CUDA graph must have every forked stream joined, and host code that
+        reads the parameters afterwards expects them updated on the current stream)."""
+        if not torch.cuda.is_available():
+            return
+        for ar in self._arenas():
+            if ar.update_event is not None:
+                (stream or torch.cuda.current_stream(ar.flat.device)).wait_event(ar.update_event)
+                ar.update_event = None

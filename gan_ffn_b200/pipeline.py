@@ -95,7 +95,7 @@ def collate_on_device(pb: PackedBatch, seq_len: Optional[int] = None, n_speakers
     from . import functional as GF
     GF._require_cuda(pb.text, "packed batch")
     L = lib()
-    S, B = int(seq_len or pb.seq_len), pb.n_dialogues
+    S, B = int(pb.seq_len if seq_len is None else seq_len), pb.n_dialogues
     if S < pb.seq_len:
         raise ValueError(f"seq_len {S} is shorter than the longest dialogue ({pb.seq_len})")
     dev, st = pb.text.device, GF._stream(pb.text)

@@ -116,6 +116,10 @@ class GANTrainer:
         self.opt_text_D = mk(text_disc, lr / 2)
         self.adversarial_loss = M.BCELoss()
         self.grad_reducer, self.world_size = grad_reducer, world_size
+        # data parallel: all-reduce + Adam of a sub-step's network run on the communication stream while the caller's
+        # stream starts the next sub-step (FusedAdam.defer_step); joined at the end of the batch
+        for o in (self.opt_acoustic_G, self.opt_acoustic_D, self.opt_visual_G, self.opt_visual_D, self.opt_text_G, self.opt_text_D):
+            o.defer_step = grad_reducer is not None
         # independent networks of a sub-step on concurrent streams (functional._Lanes); the loop bodies are unchanged
         self.overlap = overlap
         # train_disc as one discriminator pass over [real | fake] (train_disc_batched) instead of two
@@ -131,7 +135,10 @@ class GANTrainer:
         Returns the six surviving loss values as device scalars (later sub-steps overwrite earlier ones,
         as in the reference)."""
         with GF.overlap_networks(self.overlap):
-            return self._batch(data)
+            loss = self._batch(data)
+        for o in (self.opt_acoustic_G, self.opt_acoustic_D, self.opt_visual_G, self.opt_visual_D, self.opt_text_G, self.opt_text_D):
+            o.join_deferred()
+        return loss
 
     # The twelve sub-steps of train_IEMOCAP.py:355-382 in the reference's order: (kind, discriminator, generator, loss key).
     SUBSTEPS = (("D", "visual_disc", "acoustic_gen", "visual_D_loss"), ("G", "visual_disc", "acoustic_gen", "acoustic_G_loss"),
@@ -233,12 +240,15 @@ class ClassifierTrainer:
         self.overlap = overlap
         self.loss_function = M.MaskedNLLLoss(loss_weights)
         self.optimizer = FusedAdam(model, lr=lr, weight_decay=l2, grad_reducer=grad_reducer)
+        self.optimizer.defer_step = grad_reducer is not None
         self.grad_reducer = grad_reducer
 
     def step(self, data: Batch, train: bool = True):
         """One batch of the loop body (train_IEMOCAP.py:127-170).  Returns (loss, pred_, labels_)."""
         with GF.overlap_networks(self.overlap):
-            return self._step(data, train)
+            out = self._step(data, train)
+        self.optimizer.join_deferred()
+        return out
 
     def _step(self, data: Batch, train: bool = True):
         model, optimizer = self.model, self.optimizer
