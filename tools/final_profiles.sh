@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round-end measurement set (one B200): bench line, reference arm, launch list, ncu --set full captures.  Outputs under gpurun_out/.
+TAG=${1:-r2}
+python bench.py > gpurun_out/${TAG}_bench_final.json 2> gpurun_out/${TAG}_bench_final.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_step_final.csv python profiles/profile_step.py > gpurun_out/${TAG}_ncu_launches.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc --launch-skip 30 --launch-count 14 -f -o gpurun_out/${TAG}_full_gemm python profiles/profile_net.py > gpurun_out/${TAG}_ncu_full_gemm.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"attention|layernorm|reduce_ln" --launch-skip 8 --launch-count 8 -f -o gpurun_out/${TAG}_full_attn python profiles/profile_net.py > gpurun_out/${TAG}_ncu_full_attn.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"graph_build|graph_gather" --launch-skip 8 --launch-count 6 -f -o gpurun_out/${TAG}_full_graph python tools/graph_bench.py > /dev/null 2> gpurun_out/${TAG}_ncu_full_graph.log
+ls -la gpurun_out/${TAG}_*
