@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_FWD_MINB) attention_fwd_sm
   const int ir = active ? i : S - 1;
   const int kpg = (((S + 3) >> 2) + NG - 1) / NG * 4;
   const int j_beg = g * kpg, j_end = min(S, j_beg + kpg);
-  const float scale = rsqrtf((float)HD);
+  const float scale = rsqrtf((float)HD) * kLog2e;      // scores in log2 units: p = 2^(s - max)
   float q[HD];
   row_to_regs<HD>(base + (size_t)ir * ld, q, scale);   // the thread's own query row straight from global memory
   cp_async_wait_all();
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_FWD_MINB) attention_fwd_sm
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (j0 + u < j_end) {
-          const float pj = expf(s[k4 + u] - mx);
+          const float pj = ex2_f(s[k4 + u] - mx);
           lsum += pj;
           axpy_row<HD>(pj * msk[u], Vs + (j0 + u) * HD, acc);
         }
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_FWD_MINB) attention_fwd_sm
       for (int c = 0; c < HD; ++c) acc[c] += pr[c];
     }
     store_row<HD>(o + ((size_t)i * B + b) * d + (size_t)h * HD, acc, 1.f / lsum);
-    lse[(size_t)bh * S + i] = mx + logf(lsum);
+    lse[(size_t)bh * S + i] = mx * kLn2 + logf(lsum);   // natural-log lse (the C ABI's contract)
   }
 }
 
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_BWD_MINB) attention_bwd_sm
     row_to_regs<HD>(obase + (size_t)r * ldo, orow, 1.f);
     row_to_regs<HD>(dobase + (size_t)r * ldo, drow, 1.f);
     Ds[r] = dot_regs<HD>(drow, orow);
-    Ls[r] = lse[(size_t)bh * S + r];
+    Ls[r] = lse[(size_t)bh * S + r] * kLog2e;   // log2 units, like the recomputed scores below
   }
   cp_async_wait_all();
   __syncthreads();
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_BWD_MINB) attention_bwd_sm
     float acc[HD], q[HD], r[HD];
 #pragma unroll
     for (int c = 0; c < HD; ++c) acc[c] = 0.f;
-    row_to_regs<HD>(Qs + ir * HD, q, scale);
+    row_to_regs<HD>(Qs + ir * HD, q, scale * kLog2e);   // only feeds the exponent: P_ij = 2^(q'_i.k_j - lse'_i)
     row_to_regs<HD>(dOs + ir * HD, r, 1.f);
     const float Di = Ds[ir], li = Ls[ir];
     const uint64_t ebase = ((uint64_t)bh * S + ir) * S4;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_BWD_MINB) attention_bwd_sm
       for (int u = 0; u < 4; ++u) {
         const int j = j0 + u;
         if (j < j_end) {
-          const float pj = expf(dot_smem<HD>(q, Ks + j * HD) - li);
+          const float pj = ex2_f(dot_smem<HD>(q, Ks + j * HD) - li);
           const float dpd = dot_smem<HD>(r, Vs + j * HD);
           axpy_row<HD>(pj * (dpd * msk[u] - Di) * scale, Ks + j * HD, acc);
         }
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_BWD_MINB) attention_bwd_sm
 
   // ---- sweep B: dV, dK ----
   float kj[HD], vj[HD], accv[HD], acck[HD];
-  row_to_regs<HD>(Ks + ir * HD, kj, scale);   // scaled once here: P_ij = exp((k_j scale).q_i - lse_i)
+  row_to_regs<HD>(Ks + ir * HD, kj, scale * kLog2e);   // scaled once here: P_ij = 2^((k_j scale log2e).q_i - lse'_i)
   row_to_regs<HD>(Vs + ir * HD, vj, 1.f);
 #pragma unroll
   for (int c = 0; c < HD; ++c) { accv[c] = 0.f; acck[c] = 0.f; }
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(NG * 32, GANFFN_ATT_BWD_MINB) attention_bwd_sm
       if (qi < j_end) {
         const float* qrow = Qs + qi * HD;
         const float* drow = dOs + qi * HD;
-        const float p = expf(dot_smem<HD>(kj, qrow) - Ls[qi]);
+        const float p = ex2_f(dot_smem<HD>(kj, qrow) - Ls[qi]);
         const float dpd = dot_smem<HD>(vj, drow);
         axpy_row<HD>(p * m, drow, accv);
         axpy_row<HD>(p * (dpd * m - Ds[qi]) * scale, qrow, acck);

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(224) attention_fwd_mma_kernel(const float* __r
   load_head<HD>(base + 2 * d, ld, Vs, S, S8);
   cp_async_wait_all();
   __syncthreads();
-  scale_head<HD>(Qs, S16, rsqrtf((float)HD));
+  scale_head<HD>(Qs, S16, rsqrtf((float)HD) * kLog2e);   // scores in log2 units: every probability is one ex2
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(224) attention_fwd_mma_kernel(const float* __r
     dot_tile<HD>(c, qhi, qlo, Ks, 8 * n, g, t);
     const int j = 8 * n + 2 * t;
     float p[4];
-    p[0] = j < S ? expf(c[0] - mx0) : 0.f;
-    p[1] = j + 1 < S ? expf(c[1] - mx0) : 0.f;
-    p[2] = j < S ? expf(c[2] - mx1) : 0.f;
-    p[3] = j + 1 < S ? expf(c[3] - mx1) : 0.f;
+    p[0] = j < S ? ex2_f(c[0] - mx0) : 0.f;
+    p[1] = j + 1 < S ? ex2_f(c[1] - mx0) : 0.f;
+    p[2] = j < S ? ex2_f(c[2] - mx1) : 0.f;
+    p[3] = j + 1 < S ? ex2_f(c[3] - mx1) : 0.f;
     l0 += p[0] + p[1];
     l1 += p[2] + p[3];
     if (drop) {
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(224) attention_fwd_mma_kernel(const float* __r
     }
   }
   if (t == 0) {
-    if (i0 < S) lse[(size_t)blockIdx.x * S + i0] = mx0 + logf(l0);
-    if (i1 < S) lse[(size_t)blockIdx.x * S + i1] = mx1 + logf(l1);
+    if (i0 < S) lse[(size_t)blockIdx.x * S + i0] = mx0 * kLn2 + logf(l0);   // natural-log lse
+    if (i1 < S) lse[(size_t)blockIdx.x * S + i1] = mx1 * kLn2 + logf(l1);
   }
 }
 
@@ -286,14 +286,14 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
           acc = fmaf(__ldg(orow + c), __ldg(drow + c), acc);
         }
       }
-      l = lse[(size_t)blockIdx.x * S + r];
+      l = lse[(size_t)blockIdx.x * S + r] * kLog2e;   // log2 units, like the scores (Q carries log2e below)
     }
     Ds[r] = acc;
     Ls[r] = l;
   }
   cp_async_wait_all();
   __syncthreads();
-  scale_head<HD>(Qs, S16, scale);
+  scale_head<HD>(Qs, S16, scale * kLog2e);   // Q' = Q log2(e) / sqrt(hd): dK = dS^T Q' is multiplied by ln 2 at the store
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -327,10 +327,10 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
       float m[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop) frag_masks(m, key, thr, dscale, row_word0, words_per_row, 8 * n, t);
       float ds[4];
-      ds[0] = j < S ? expf(c[0] - L0) * (e[0] * m[0] - D0) : 0.f;
-      ds[1] = j + 1 < S ? expf(c[1] - L0) * (e[1] * m[1] - D0) : 0.f;
-      ds[2] = j < S ? expf(c[2] - L1) * (e[2] * m[2] - D1) : 0.f;
-      ds[3] = j + 1 < S ? expf(c[3] - L1) * (e[3] * m[3] - D1) : 0.f;
+      ds[0] = j < S ? ex2_f(c[0] - L0) * (e[0] * m[0] - D0) : 0.f;
+      ds[1] = j + 1 < S ? ex2_f(c[1] - L0) * (e[1] * m[1] - D0) : 0.f;
+      ds[2] = j < S ? ex2_f(c[2] - L1) * (e[2] * m[2] - D1) : 0.f;
+      ds[3] = j + 1 < S ? ex2_f(c[3] - L1) * (e[3] * m[3] - D1) : 0.f;
       acc_tile<HD>(acc, ds, Ks, 8 * n, g, t);
     }
 #pragma unroll
@@ -377,10 +377,10 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
       }
       const bool va = q < S, vb = q + 1 < S;
       float p[4], pm[4], ds[4];
-      p[0] = va ? expf(c[0] - La) : 0.f;
-      p[1] = vb ? expf(c[1] - Lb) : 0.f;
-      p[2] = va ? expf(c[2] - La) : 0.f;
-      p[3] = vb ? expf(c[3] - Lb) : 0.f;
+      p[0] = va ? ex2_f(c[0] - La) : 0.f;
+      p[1] = vb ? ex2_f(c[1] - Lb) : 0.f;
+      p[2] = va ? ex2_f(c[2] - La) : 0.f;
+      p[3] = vb ? ex2_f(c[3] - Lb) : 0.f;
       pm[0] = p[0] * m[0]; pm[1] = p[1] * m[1]; pm[2] = p[2] * m[2]; pm[3] = p[3] * m[3];
       ds[0] = p[0] * (e[0] * m[0] - Da);
       ds[1] = p[1] * (e[1] * m[1] - Db);
@@ -395,11 +395,11 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
       if (c < HD) {
         if (i0 < S) {
           *reinterpret_cast<float2*>(out0 + 2 * d + c) = make_float2(accv[nn][0], accv[nn][1]);
-          *reinterpret_cast<float2*>(out0 + d + c) = make_float2(acck[nn][0], acck[nn][1]);
+          *reinterpret_cast<float2*>(out0 + d + c) = make_float2(acck[nn][0] * kLn2, acck[nn][1] * kLn2);
         }
         if (i1 < S) {
           *reinterpret_cast<float2*>(out1 + 2 * d + c) = make_float2(accv[nn][2], accv[nn][3]);
-          *reinterpret_cast<float2*>(out1 + d + c) = make_float2(acck[nn][2], acck[nn][3]);
+          *reinterpret_cast<float2*>(out1 + d + c) = make_float2(acck[nn][2] * kLn2, acck[nn][3] * kLn2);
         }
       }
     }

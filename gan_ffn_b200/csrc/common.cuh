@@ -136,6 +136,16 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * inv_sqrt_2pi * expf(-0.5f * x * x);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 2^x in one MUFU instruction (rel. error ~2^-22).  The attention kernels keep their scores in log2 units (the 1/sqrt(hd)
+// scale of Q carries a log2(e) factor) so that every probability is a single ex2: expf() is ~12 instructions, and the
+// small-head kernels are bound by instruction issue (one or two exponentials per (query, key) pair of 45 - 110 instructions).
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
