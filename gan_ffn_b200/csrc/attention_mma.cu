@@ -17,16 +17,13 @@
 //
 // Reference: F.scaled_dot_product_attention inside nn.MultiheadAttention (torch functional.py
 // multi_head_attention_forward), dropout on the probabilities; padded slots are real tokens.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ganffn {
 namespace {
 
-__device__ __forceinline__ uint32_t tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return tf32_rna_bits(x); }
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
   hi = tf32_hi(x);
   lo = __float_as_uint(x - __uint_as_float(hi));   // the tensor core reads the top 19 bits: lo is truncated, |err| <= 2^-21 |x|
@@ -248,7 +245,7 @@ template <int HD>
 __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
     const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
     const float* __restrict__ d_o, float* __restrict__ dqkv, int S, int B, int d, int nhead, float p_drop,
-    const Seed seed_ref, uint32_t site) {
+    const Seed seed_ref, uint32_t site, int parts) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = Dims<HD>::LD, KS = Dims<HD>::KS;
   const int S16 = (S + 15) & ~15;
@@ -258,7 +255,11 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
   float* dOs = Vs + S16 * LD;
   float* Ls = dOs + S16 * LD;       // [S16] row log-sum-exp
   float* Ds = Ls + S16;             // [S16] rowsum(dO * O)
-  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  // `parts` CTAs may share one (dialogue, head), each staging all four tiles and owning a contiguous range of 16-row
+  // strips (tuning knob GANFFN_ATTN_BWD_PARTS; head_dim 64 needs ~250 registers per thread, i.e. one 192-thread CTA per
+  // SM and two waves for the 256 CTAs of an S=94, B=32 layer -- but splitting did not pay: see the launcher).
+  const int bh = blockIdx.x / parts, part = blockIdx.x % parts;
+  const int b = bh / nhead, h = bh % nhead;
   const int ld = B * 3 * d, ldo = B * d;
   const float scale = rsqrtf((float)HD);
   const float* base = qkv + (size_t)b * 3 * d + (size_t)h * HD;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
           acc = fmaf(__ldg(orow + c), __ldg(drow + c), acc);
         }
       }
-      l = lse[(size_t)blockIdx.x * S + r] * kLog2e;   // log2 units, like the scores (Q carries log2e below)
+      l = lse[(size_t)bh * S + r] * kLog2e;   // log2 units, like the scores (Q carries log2e below)
     }
     Ds[r] = acc;
     Ls[r] = l;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int r0 = warp * 16;
+  const int r0 = (part * (int)(blockDim.x >> 5) + warp) * 16;
   if (r0 >= S) return;
   const int nt = S16 >> 3;
   const bool drop = p_drop > 0.f;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
     load_a_frags<HD>(Qs, r0, g, t, qhi, qlo);
     load_a_frags<HD>(dOs, r0, g, t, ghi, glo);
     const float L0 = Ls[i0], L1 = Ls[i1], D0 = Ds[i0], D1 = Ds[i1];
-    const uint64_t row_word0 = ((uint64_t)blockIdx.x * S + (uint64_t)i0) * words_per_row;
+    const uint64_t row_word0 = ((uint64_t)bh * S + (uint64_t)i0) * words_per_row;
     float acc[KS][4];
 #pragma unroll
     for (int nn = 0; nn < KS; ++nn) acc[nn][0] = acc[nn][1] = acc[nn][2] = acc[nn][3] = 0.f;
@@ -366,8 +367,8 @@ __global__ void __launch_bounds__(224) attention_bwd_mma_kernel(
       const float La = Ls[q], Lb = Ls[q + 1], Da = Ds[q], Db = Ds[q + 1];
       float m[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop) {
-        const uint64_t rowa = ((uint64_t)blockIdx.x * S + (uint64_t)min(q, S - 1)) * words_per_row;
-        const uint64_t rowb = ((uint64_t)blockIdx.x * S + (uint64_t)min(q + 1, S - 1)) * words_per_row;
+        const uint64_t rowa = ((uint64_t)bh * S + (uint64_t)min(q, S - 1)) * words_per_row;
+        const uint64_t rowb = ((uint64_t)bh * S + (uint64_t)min(q + 1, S - 1)) * words_per_row;
         const uint64_t wa0 = drop_word(key, rowa + wk0), wb0 = drop_word(key, rowb + wk0);
         const uint64_t wa1 = drop_word(key, rowa + wk1), wb1 = drop_word(key, rowb + wk1);
         m[0] = ((uint32_t)(wa0 >> sh0) & 0xFFFFu) >= thr ? dscale : 0.f;   // key i0, query q
@@ -425,8 +426,13 @@ static int launch_bwd_mma(const float* qkv, const float* o, const float* lse, co
                           int nhead, float p, Seed seed, int site, cudaStream_t st) {
   auto bytes = [](int s) { const int s16 = (s + 15) & ~15; return ((size_t)4 * s16 * Dims<HD>::LD + 2 * s16) * sizeof(float); };
   GANFFN_SMEM_OPTIN(attention_bwd_mma_kernel<HD>, bytes(GANFFN_MAX_SEQ));
-  attention_bwd_mma_kernel<HD><<<B * nhead, mma_threads(S), bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
-                                                                            (uint32_t)site);
+  static const int parts_env = getenv("GANFFN_ATTN_BWD_PARTS") ? atoi(getenv("GANFFN_ATTN_BWD_PARTS")) : 0;   // A/B switch
+  const int strips = (S + 15) / 16;
+  int parts = parts_env > 0 ? parts_env : 1;   // measured (r2, S=94 B=32 head_dim 64): 1 / 2 / 3 parts = 80 / 87 / 103 us -- every CTA stages all four tiles
+  parts = std::min(parts, strips);
+  const int warps = (strips + parts - 1) / parts;
+  attention_bwd_mma_kernel<HD><<<B * nhead * parts, warps * 32, bytes(S), st>>>(qkv, o, lse, d_o, dqkv, S, B, d, nhead, p, seed,
+                                                                                (uint32_t)site, parts);
   GANFFN_LAUNCHED("attention_bwd_mma_kernel");
   return GANFFN_OK;
 }

@@ -136,6 +136,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * inv_sqrt_2pi * expf(-0.5f * x * x);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Round-to-nearest (ties away from zero) of an fp32 value to TF32, as two integer instructions: add half a TF32 ulp to
+// the magnitude bits and clear the 13 low mantissa bits -- the carry propagates into the exponent exactly as rounding
+// requires.  Bit-identical to `cvt.rna.tf32.f32` for finite inputs (Inf stays Inf), which on sm_100a compiles to a
+// five-to-six instruction sequence (VIADD, LOP3, FSETP, SEL, ...: r2 SASS of attention_bwd_mma_kernel<64> -- 45 % of its
+// 26.6 M warp instructions were the conversions of the 3xTF32 operand splits).
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
 // 2^x in one MUFU instruction (rel. error ~2^-22).  The attention kernels keep their scores in log2 units (the 1/sqrt(hd)
 // scale of Q carries a log2(e) factor) so that every probability is a single ex2: expf() is ~12 instructions, and the
 // small-head kernels are bound by instruction issue (one or two exponentials per (query, key) pair of 45 - 110 instructions).

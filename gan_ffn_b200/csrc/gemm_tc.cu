@@ -132,11 +132,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return tf32_rna_bits(x); }   // common.cuh: two integer instructions
 
 // Shared-memory matrix descriptor (sm_100 UMMA), version 1.
 //   K-major, SWIZZLE_128B: rows of 128 B (32 tf32 along K), 8-row atoms of 1024 B, 16-byte chunk index
