@@ -75,8 +75,10 @@ int gemm(const float* A, int lda, bool transA, const float* B, int ldb, bool b_i
     Epilogue e2 = ep;
     e2.rowsum = nullptr;
     e2.ln_out = nullptr;
+    e2.lnb_dz = nullptr;
     rc = gemm_simt(A, lda, transA, B, ldb, b_is_nk, C, ldc, M, N, K, e2, scratch, scratch_floats, st);
     if (rc == GANFFN_OK && ep.ln_out) rc = layernorm_fwd(C, ep.ln_gamma, ep.ln_beta, ep.ln_out, M, N, st);   // not fused on the FFMA engine
+    if (rc == GANFFN_OK && ep.lnb_dz) rc = layernorm_bwd_after(ep, C, M, N, st);
   }
   if (g_prof) {
     prof_record(pe.b, st);

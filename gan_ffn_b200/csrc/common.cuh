@@ -222,6 +222,21 @@ struct Epilogue {
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float* ln_out = nullptr;
+  // LayerNorm BACKWARD behind a data-gradient product: the product's result (residual included) is dy of a post-norm
+  // LayerNorm x = LN(z).  When lnb_dz is set, gemm() also computes dz = dLN(dy; z, gamma) -> lnb_dz, the dropout-masked
+  // branch gradient dz * mask(lnb_site) -> lnb_dzd (optional), and accumulates dgamma / dbeta / the sublayer's bias
+  // gradient (column sums of dy * xhat, dy, dz * mask; optional).  The tcgen05 engine does it inside its split-K fold
+  // (N <= 128); every other case runs layernorm_bwd() behind the product -- same results.
+  const float* lnb_z = nullptr;
+  const float* lnb_gamma = nullptr;
+  float* lnb_dz = nullptr;
+  float* lnb_dzd = nullptr;
+  float* lnb_dgamma = nullptr;
+  float* lnb_dbeta = nullptr;
+  float* lnb_dbias = nullptr;
+  float lnb_p = 0.0f;
+  uint32_t lnb_site = 0;
+  Seed lnb_seed;
 };
 
 // Applies the epilogue to the four accumulators of row m, columns n..n+3 (n % 4 == 0) and

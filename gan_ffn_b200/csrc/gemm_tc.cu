@@ -1056,6 +1056,84 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_ln_kernel(const float* _
   }
 }
 
+// Split-K fold + residual + LayerNorm BACKWARD (N <= 128, N % 4 == 0): the folded product is dy of x = LN(z); warp = row,
+// lane = one float4 of the row, two rows per warp; the column sums (dgamma, dbeta, bias gradient of the sublayer) are
+// folded across the block's warps in shared memory and added to the arena with one red.global.add per column and block.
+// Replaces the fold and the stand-alone LayerNorm-backward launch behind the d <= 128 FFN's dX = dH W1 product.
+constexpr int LNB_ROWS = 16;   // rows per 256-thread block
+__global__ void __launch_bounds__(256) tc_splitk_reduce_lnb_kernel(const float* __restrict__ partial, int splits, float* C,
+                                                                   int ldc, int M, int N, int Np, const Epilogue ep) {
+  __shared__ float4 red[8][3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = 4 * lane;
+  const bool on = n < N;
+  const float inv_n = 1.0f / (float)N;
+  const float4 gm = on ? __ldg(reinterpret_cast<const float4*>(ep.lnb_gamma + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool drop = ep.lnb_dzd != nullptr && ep.lnb_p > 0.0f;
+  const uint64_t seed = drop ? seed_value(ep.lnb_seed) : 0ull;
+  const float dscale = drop ? 1.0f / (1.0f - ep.lnb_p) : 1.0f;
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, ds = dg;
+#pragma unroll
+  for (int rr = 0; rr < LNB_ROWS / 8; ++rr) {
+    const int m = blockIdx.x * LNB_ROWS + rr * 8 + warp;
+    if (m >= M) continue;                       // warp-uniform
+    float4 dy = make_float4(0.f, 0.f, 0.f, 0.f), z = dy;
+    if (on) {
+      for (int zi = 0; zi < splits; ++zi) {
+        const float4 q = *reinterpret_cast<const float4*>(partial + ((size_t)zi * M + m) * Np + n);
+        dy.x += q.x; dy.y += q.y; dy.z += q.z; dy.w += q.w;
+      }
+      if (ep.residual) {
+        const float4 r4 = *reinterpret_cast<const float4*>(ep.residual + (size_t)m * ep.ldr + n);
+        dy.x += r4.x; dy.y += r4.y; dy.z += r4.z; dy.w += r4.w;
+      }
+      z = *reinterpret_cast<const float4*>(ep.lnb_z + (size_t)m * ldc + n);
+      *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = dy;
+    }
+    const float mean = warp_sum(z.x + z.y + z.z + z.w) * inv_n;
+    float sq = 0.f;
+    if (on) { z.x -= mean; z.y -= mean; z.z -= mean; z.w -= mean; sq = z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w; }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_n + TC_LN_EPS);
+    float s1 = 0.f, s2 = 0.f;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      z.x *= rstd; z.y *= rstd; z.z *= rstd; z.w *= rstd;       // xhat
+      dg.x += dy.x * z.x; dg.y += dy.y * z.y; dg.z += dy.z * z.z; dg.w += dy.w * z.w;
+      db.x += dy.x; db.y += dy.y; db.z += dy.z; db.w += dy.w;
+      g = make_float4(dy.x * gm.x, dy.y * gm.y, dy.z * gm.z, dy.w * gm.w);
+      s1 = g.x + g.y + g.z + g.w;
+      s2 = g.x * z.x + g.y * z.y + g.z * z.z + g.w * z.w;
+    }
+    s1 = warp_sum(s1) * inv_n;
+    s2 = warp_sum(s2) * inv_n;
+    if (on) {
+      float4 o = make_float4(rstd * (g.x - s1 - z.x * s2), rstd * (g.y - s1 - z.y * s2), rstd * (g.z - s1 - z.z * s2),
+                             rstd * (g.w - s1 - z.w * s2));
+      *reinterpret_cast<float4*>(ep.lnb_dz + (size_t)m * ldc + n) = o;
+      if (drop) {
+        float msk[4];
+        dropout_scale4(seed, ep.lnb_site, (uint64_t)m * (uint64_t)N + (uint64_t)n, ep.lnb_p, dscale, msk);
+        o = make_float4(o.x * msk[0], o.y * msk[1], o.z * msk[2], o.w * msk[3]);
+        *reinterpret_cast<float4*>(ep.lnb_dzd + (size_t)m * ldc + n) = o;
+      }
+      ds.x += o.x; ds.y += o.y; ds.z += o.z; ds.w += o.w;
+    }
+  }
+  red[warp][0][lane] = dg;
+  red[warp][1][lane] = db;
+  red[warp][2][lane] = ds;
+  __syncthreads();
+  for (int c = threadIdx.x; c < 3 * N; c += blockDim.x) {
+    const int seg = c / N, col = c - seg * N;
+    float* out = seg == 0 ? ep.lnb_dgamma : seg == 1 ? ep.lnb_dbeta : ep.lnb_dbias;
+    if (out == nullptr) continue;
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sacc += reinterpret_cast<const float*>(&red[w][seg][0])[col];
+    atomicAdd(out + col, sacc);
+  }
+}
+
 struct TcPlan { int splits; int kps; };
 
 // Split-K for an accumulating (red.global.add) product: no fold kernel, so the only costs are the per-CTA
@@ -1217,6 +1295,7 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     GANFFN_TRY(b_is_nk ? launch_astat2<true>(p, epi, dim3(groups, mtiles, 1), st)
                        : launch_astat2<false>(p, epi, dim3(groups, mtiles, 1), st));
     if (ep.ln_out) GANFFN_TRY(layernorm_fwd(C, ep.ln_gamma, ep.ln_beta, ep.ln_out, M, N, st));
+    if (ep.lnb_dz) GANFFN_TRY(layernorm_bwd_after(ep, C, M, N, st));
     return GANFFN_OK;
   }
   TcPlan pl = tc_plan(M, N, K);
@@ -1242,11 +1321,20 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
   const bool ln_in_kernel = ln_simple && pl.splits == 1 && epi != EPI_FULL;
   const bool ln_in_fold = ln_simple && pl.splits > 1;
   if (!ln_in_kernel) p.ep.ln_out = nullptr;
+  // LayerNorm backward behind the product (Epilogue::lnb_dz): inside the split-K fold, else stand-alone
+  const bool lnb = ep.lnb_dz != nullptr;
+  const bool lnb_in_fold = lnb && !ln_fuse_off && !g_deterministic && pl.splits > 1 && N <= BN && (N & 3) == 0 && ldc == N &&
+                           ep.act == GANFFN_ACT_NONE && ep.dact == DACT_NONE && !ep.pre && ep.beta == 0.0f && !ep.bias &&
+                           ep.p_drop == 0.0f && !ln && al16(C) && al16(ep.lnb_z) && al16(ep.lnb_gamma) && al16(ep.lnb_dz) &&
+                           (!ep.lnb_dzd || al16(ep.lnb_dzd)) && (!ep.residual || ((ep.ldr & 3) == 0 && al16(ep.residual)));
   GANFFN_TRY(launch_tc(p, transA, b_is_nk, epi, grid, st));
   if (pl.splits > 1) {
     if (ln_in_fold) {
       tc_splitk_reduce_ln_kernel<<<cdiv(M, 8), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
       GANFFN_LAUNCHED("tc_splitk_reduce_ln_kernel");
+    } else if (lnb_in_fold) {
+      tc_splitk_reduce_lnb_kernel<<<cdiv(M, LNB_ROWS), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
+      GANFFN_LAUNCHED("tc_splitk_reduce_lnb_kernel");
     } else {
       const int64_t nvec = (int64_t)M * (Np / 4);
       tc_splitk_reduce_kernel<<<cdiv(nvec, 256), 256, 0, st>>>(scratch, pl.splits, C, ldc, M, N, Np, ep);
@@ -1254,6 +1342,7 @@ int gemm_tc(const float* A, int lda, bool transA, const float* B, int ldb, bool 
     }
   }
   if (ln && !ln_in_kernel && !ln_in_fold) GANFFN_TRY(layernorm_fwd(C, ep.ln_gamma, ep.ln_beta, ep.ln_out, M, N, st));
+  if (lnb && !lnb_in_fold) GANFFN_TRY(layernorm_bwd_after(ep, C, M, N, st));
   return GANFFN_OK;
 }
 

@@ -33,6 +33,8 @@ int layernorm_fwd(const float* z, const float* gamma, const float* beta, float* 
 int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dz_drop, float* dgamma,
                   float* dbeta, float* dbias_sub, int T, int d, int accumulate, float p, Seed seed, int site,
                   cudaStream_t st);
+// the stand-alone LayerNorm backward behind a product whose Epilogue asked for it (lnb_* fields) and could not fuse it
+int layernorm_bwd_after(const Epilogue& ep, const float* dy, int M, int N, cudaStream_t st);
 int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, Seed seed, cudaStream_t st);
 enum { EW_GELU_DROP = 0, EW_DGELU_MASK = 1, EW_DSIGMOID_MASK = 2, EW_MASK = 3 };
 int elementwise(const float* a, const float* src, float* y, int64_t n, int mode, float p, Seed seed, int site,

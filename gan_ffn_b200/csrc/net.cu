@@ -371,14 +371,16 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
       GANFFN_TRY(cx.dgrad(dzd, P(lo[L2_W]), scratch + sc.dh, T, d, nd.dff, ep));
     }
     GANFFN_TRY(wgrad_side(W_L1, scratch + sc.dh, base + sl.x1, G(lo[L1_W]), G(lo[L1_B]), T, nd.dff, d));
+    // x1 = LN1(z1), z1 = xin + drop(out_proj(o)): the LayerNorm-1 backward rides behind the product that makes its dy
+    // (Epilogue::lnb_*: inside the split-K fold on the tcgen05 engine, stand-alone otherwise)
+    wait_slot(W_OUT);     // the weight-gradient stream may still be reading dz1 / dzd1 of the layer above
     {
       Epilogue ep; ep.residual = dz; ep.ldr = d;
+      ep.lnb_z = base + sl.z1; ep.lnb_gamma = P(lo[N1_W]); ep.lnb_dz = dz1; ep.lnb_dzd = p_enc > 0.f ? dzd1_buf : nullptr;
+      ep.lnb_dgamma = G(lo[N1_W]); ep.lnb_dbeta = G(lo[N1_B]); ep.lnb_dbias = G(lo[OUT_B]);
+      ep.lnb_p = p_enc; ep.lnb_seed = seed; ep.lnb_site = GANFFN_SITE_LAYER(l, 1);
       GANFFN_TRY(cx.dgrad(scratch + sc.dh, P(lo[L1_W]), db, T, nd.dff, d, ep));
     }
-    // x1 = LN1(z1), z1 = xin + drop(out_proj(o))
-    wait_slot(W_OUT);
-    GANFFN_TRY(layernorm_bwd(db, base + sl.z1, P(lo[N1_W]), dz1, p_enc > 0.f ? dzd1_buf : nullptr, G(lo[N1_W]), G(lo[N1_B]),
-                             G(lo[OUT_B]), T, d, 1, p_enc, seed, GANFFN_SITE_LAYER(l, 1), st));
     GANFFN_TRY(wgrad_side(W_OUT, dzd1, base + sl.o, G(lo[OUT_W]), nullptr, T, d, d));
     GANFFN_TRY(cx.dgrad(dzd1, P(lo[OUT_W]), scratch + sc.d_o, T, d, d, Epilogue{}));
     wait_slot(W_IN);

@@ -352,6 +352,11 @@ int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz
   return GANFFN_OK;
 }
 
+int layernorm_bwd_after(const Epilogue& ep, const float* dy, int M, int N, cudaStream_t st) {
+  return layernorm_bwd(dy, ep.lnb_z, ep.lnb_gamma, ep.lnb_dz, ep.lnb_p > 0.f ? ep.lnb_dzd : nullptr, ep.lnb_dgamma, ep.lnb_dbeta,
+                       ep.lnb_dbias, M, N, 1, ep.lnb_p, ep.lnb_seed, (int)ep.lnb_site, st);
+}
+
 int posenc_fwd(const float* x, const float* pe, float* y, int S, int B, int d, float p, Seed seed, cudaStream_t st) {
   GANFFN_CHECK_ARG(S >= 1 && S <= GANFFN_MAX_SEQ, "posenc: seq_len %d outside [1,%d] (model.py:1179)", S, GANFFN_MAX_SEQ);
   GANFFN_CHECK_ARG(d % 4 == 0, "posenc: d=%d must be a multiple of 4", d);
