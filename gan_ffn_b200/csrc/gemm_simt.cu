@@ -178,7 +178,13 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = Np >> 2;
   if (idx >= (int64_t)M * nq) return;
-  const int m = (int)(idx / nq), n = (int)(idx % nq) * 4;
+  int m, n;
+  if ((int64_t)M * nq < (int64_t)1 << 31) {   // 32-bit index arithmetic (a 64-bit divide costs more than the fold itself)
+    const unsigned i32 = (unsigned)idx, mq = i32 / (unsigned)nq;
+    m = (int)mq; n = (int)(i32 - mq * (unsigned)nq) * 4;
+  } else {
+    m = (int)(idx / nq); n = (int)(idx % nq) * 4;
+  }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int z = 0; z < splits; ++z) {
     float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)z * M + m) * Np + n);

@@ -202,6 +202,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <bool KMAJ>
 __device__ __forceinline__ void load_a(float (&v)[16], const float* __restrict__ q, int lda, int rows_left, int k_left) {
   if (KMAJ) {
+    const bool interior = rows_left > 24 && k_left > 8;   // every one of the eight loads is in range
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -209,16 +210,21 @@ __device__ __forceinline__ void load_a(float (&v)[16], const float* __restrict__
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           float2 x = make_float2(0.f, 0.f);
-          if (16 * h + 8 * rr < rows_left && 8 * cg < k_left)
+          if (interior || (16 * h + 8 * rr < rows_left && 8 * cg < k_left))
             x = __ldg(reinterpret_cast<const float2*>(q + (size_t)(16 * h + 8 * rr) * lda + 8 * cg));
           v[8 * h + 4 * cg + 2 * rr] = x.x;
           v[8 * h + 4 * cg + 2 * rr + 1] = x.y;
         }
   } else {
+    if (rows_left > 0 && k_left >= 16) {   // interior block: sixteen unpredicated loads at a constant stride
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[j] = 0.f;
-      if (rows_left > 0 && j < k_left) v[j] = __ldg(q + (size_t)j * lda);
+      for (int j = 0; j < 16; ++j) v[j] = __ldg(q + (size_t)j * lda);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = 0.f;
+        if (rows_left > 0 && j < k_left) v[j] = __ldg(q + (size_t)j * lda);
+      }
     }
   }
 }
@@ -258,6 +264,12 @@ constexpr int BCH = BN * 8 / NB;
 template <bool KMAJ>
 __device__ __forceinline__ void load_b(float4 (&v)[BCH], const float* __restrict__ q, int64_t istride, int rows_left,
                                        int k_left) {
+  const bool interior = KMAJ ? (rows_left > 32 * (BCH - 1) && k_left > 0) : (rows_left > 0 && k_left > 8 * (BCH - 1));
+  if (interior) {
+#pragma unroll
+    for (int i = 0; i < BCH; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(q + (size_t)i * istride));
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < BCH; ++i) {
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1001,7 +1013,13 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __re
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = Np >> 2;
   if (idx >= (int64_t)M * nq) return;
-  const int m = (int)(idx / nq), n = (int)(idx % nq) * 4;
+  int m, n;
+  if ((int64_t)M * nq < (int64_t)1 << 31) {   // 32-bit index arithmetic (a 64-bit divide costs more than the fold itself)
+    const unsigned i32 = (unsigned)idx, mq = i32 / (unsigned)nq;
+    m = (int)mq; n = (int)(i32 - mq * (unsigned)nq) * 4;
+  } else {
+    m = (int)(idx / nq); n = (int)(idx % nq) * 4;
+  }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int z = 0; z < splits; ++z) {
     const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)z * M + m) * Np + n);
