@@ -181,24 +181,26 @@ class BiModel(nn.Module):
         self.matchatt = MatchingAttention(2 * D_e, 2 * D_e, att_type="general2")
 
     @staticmethod
-    def _reverse_seq(X, mask):
+    def _reverse_seq(X, mask, max_len=None):
         """X (S, B, D), mask (B, S): each dialogue's first ``len`` steps reversed, zero beyond; output length
-        max(len) (what flipping each prefix and ``pad_sequence`` gives, model.py:1019-1031)."""
+        max(len) (what flipping each prefix and ``pad_sequence`` gives, model.py:1019-1031).  ``max_len``: the longest
+        dialogue when the caller knows it on the host (the loader's ``lengths``) -- avoids reading it back from the
+        device, which also makes the head recordable into a CUDA graph."""
         lens = mask.sum(1).int()                                             # (B,)
-        L = int(lens.max().item()) if lens.numel() else 0
+        L = int(max_len) if max_len is not None else (int(lens.max().item()) if lens.numel() else 0)
         t = torch.arange(L, device=X.device).unsqueeze(1)                    # (L, 1)
         src = lens.unsqueeze(0).long() - 1 - t                               # (L, B)
         valid = src >= 0
         idx = src.clamp(min=0).unsqueeze(2).expand(-1, -1, X.size(2))
         return X.gather(0, idx) * valid.unsqueeze(2).to(X.dtype)
 
-    def forward(self, U, qmask, umask, att2=True):
+    def forward(self, U, qmask, umask, att2=True, max_len=None):
         emotions_f, alpha_f = self.dialog_rnn_f(U, qmask)
         emotions_f = self.dropout_rec(emotions_f)
-        rev_U = self._reverse_seq(U, umask)
-        rev_qmask = self._reverse_seq(qmask, umask)
+        rev_U = self._reverse_seq(U, umask, max_len)
+        rev_qmask = self._reverse_seq(qmask, umask, max_len)
         emotions_b, alpha_b = self.dialog_rnn_r(rev_U, rev_qmask)
-        emotions_b = self._reverse_seq(emotions_b, umask)
+        emotions_b = self._reverse_seq(emotions_b, umask, max_len)
         emotions_b = self.dropout_rec(emotions_b)
         emotions = torch.cat([emotions_f, emotions_b], dim=-1)
         if att2:

@@ -272,9 +272,11 @@ class GAN_FFN_DialogueRNN(nn.Module):
         GF.join_lanes()   # the sum below is a plain torch op on the caller's stream
         return acoustic_fusion + visual_fusion + text_fusion
 
-    def forward(self, acoustic, visual, text, qmask, umask):
+    def forward(self, acoustic, visual, text, qmask, umask, max_len=None):
+        """``max_len`` (optional, beyond the reference's signature): the longest dialogue of the batch as a host integer
+        (the loader's ``lengths``); without it the head reads it back from ``umask`` (a device synchronisation)."""
         fusion = self.fusion(acoustic, visual, text)
-        log_prob, alpha, alpha_f, alpha_b = self.bi_model(fusion, qmask, umask)
+        log_prob, alpha, alpha_f, alpha_b = self.bi_model(fusion, qmask, umask, max_len=max_len)
         return log_prob, alpha, alpha_f, alpha_b
 
 

@@ -233,7 +233,8 @@ class GANTrainer:
 
 
 class ClassifierTrainer:
-    """Stage 2 (reference ``train_or_eval_model``, train_IEMOCAP.py:103-197) for ``GAN_FFN``."""
+    """Stage 2 (reference ``train_or_eval_model``, train_IEMOCAP.py:103-197) for ``GAN_FFN``, and the same loop body of
+    train_IEMOCAP_DialogueRNN.py for ``GAN_FFN_DialogueRNN`` (the model is then called with ``qmask`` and ``umask`` too)."""
 
     def __init__(self, model: M.GAN_FFN, loss_weights=None, lr=FFN_LR, l2=FFN_L2, grad_reducer=None, overlap: bool = True):
         self.model = model
@@ -268,7 +269,10 @@ class ClassifierTrainer:
             # the override is scoped to this call: a later eval step must get the plain local mean again
             self.loss_function.den_override = 1.0 if den is not None else 0.0
             with torch.set_grad_enabled(train):
-                log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf)
+                if isinstance(model, M.GAN_FFN_DialogueRNN):
+                    log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf, data.qmask, umask, max_len=max(data.lengths))
+                else:
+                    log_prob, alpha, alpha_f, alpha_b = model(acouf, visuf, textf)
                 lp_ = log_prob.transpose(0, 1).contiguous().view(-1, log_prob.size()[2])
                 labels_ = label.view(-1)
                 loss = self.loss_function(lp_, labels_, umask)
@@ -338,7 +342,8 @@ class GraphedTrainStep:
             self.seeds = GF.DeviceSeedStream(dev, base=self.seed)
         prev = GF.set_seed_stream(self.seeds)
         try:
-            key = (tuple(batch.text.shape), tuple(batch.visual.shape), dev.index)
+            # max(lengths): the DialogueRNN head bakes the longest dialogue into the recording (BiModel._reverse_seq)
+            key = (tuple(batch.text.shape), tuple(batch.visual.shape), dev.index, max(batch.lengths) if batch.lengths else 0)
             self.last_key = key
             if not self.enabled or key not in self._seen:
                 self._seen.add(key)

@@ -94,3 +94,37 @@ def test_gan_ffn_dialogue_rnn_matches_reference_fixture():
     for gen in (ga, gv, gt):
         g = gen.arena().grad
         assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_dialogue_rnn_trainer_step_eager_and_graph_replay_agree():
+    """ClassifierTrainer over GAN_FFN_DialogueRNN (the train_IEMOCAP_DialogueRNN.py loop body): the step recorded into
+    a CUDA graph (the head gets the longest dialogue from the host, so nothing is read back) equals the eager step."""
+    import gan_ffn_b200 as G
+    from gan_ffn_b200 import synthetic, train
+
+    def build():
+        torch.manual_seed(SEED)
+        ga, gv, gt = G.AcousticGenerator(100), G.VisualGenerator(100), G.TextGenerator(100)
+        m = G.GAN_FFN_DialogueRNN(ga, gv, gt, 100, 50, 50, 40, 40, 30, 6, False, "general", 0.1, 0.6).to("cuda")
+        cls = train.ClassifierTrainer(m, torch.tensor(synthetic.IEMOCAP_LOSS_WEIGHTS, device="cuda"))
+        for mod in m.modules():                      # dropout off everywhere: the two runs must be comparable
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        m.train = lambda mode=True: torch.nn.Module.train(m, False)   # keep the generators' kernels in eval mode
+        return m, cls
+
+    batch = synthetic.make_batch(n_dialogues=3, lengths=[12, 7, 10], seed=SEED).to("cuda")
+    m1, eager = build()
+    m2, graphed = build()
+    stepper = train.GraphedTrainStep(None, graphed, seed=1)
+    for it in range(3):
+        l1, p1, _ = eager.step(batch, train=True)
+        out = stepper(batch)
+        assert abs(float(l1) - float(out["loss"])) <= 1e-4 * abs(float(l1)), (it, float(l1), float(out["loss"]))
+        assert torch.equal(p1, out["pred"])
+    assert stepper.kernels_per_replay, "the third call must have been a graph replay"
+    torch.cuda.synchronize()
+    for (n1, a), (n2, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert n1 == n2
+        assert float((a.detach() - b.detach()).abs().max()) <= 3 * 2e-4 * 1.001, n1      # three Adam steps of lr 1e-4 at most
