@@ -64,6 +64,12 @@ int adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2, float eps,
               float wd, float gscale, cudaStream_t st);
 
+// head.cu: the discriminator head (gelu -> fc1 -> fc2 -> fc3 -> sigmoid, model.py:1320-1327) as one kernel
+bool disc_head_fusable(int d, int h1, int h2);
+int disc_head_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                  const float* b3, float* g0, float* f1, float* a1, float* f2, float* a2, float* out, int T, int d, float p_drop,
+                  Seed seed, int site0, cudaStream_t st);
+
 // net.cu
 struct NetDims {
   int kind, S, B, d_in, d, nhead, dff, L, h1, h2;

@@ -241,6 +241,10 @@ int net_fwd(const NetDims& nd, const float* params, const int64_t* off, const fl
 
   // head
   const bool gen = nd.kind == GANFFN_NET_GENERATOR;
+  if (!gen && disc_head_fusable(d, nd.h1, nd.h2))   // the whole 100 -> 64 -> 16 -> 1 discriminator head in one kernel (head.cu)
+    return disc_head_fwd(cur, P(hoff[FC1_W]), P(hoff[FC1_B]), P(hoff[FC2_W]), P(hoff[FC2_B]), P(hoff[FC3_W]), P(hoff[FC3_B]),
+                         stash + sl.g0, stash + sl.f1, stash + sl.a1, stash + sl.f2, stash + sl.a2, out, T, d, p_hd, seed,
+                         GANFFN_SITE_HEAD, st);
   GANFFN_TRY(elementwise(cur, nullptr, stash + sl.g0, (int64_t)T * d, EW_GELU_DROP, gen ? p_hd : 0.f, seed,
                          GANFFN_SITE_HEAD + 0, st));
   {

@@ -9,7 +9,7 @@ obj=/tmp/ganffn_variant_$(basename "$out" .so)
 mkdir -p "$obj"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 pids=()
-for f in capi gemm_simt gemm_tc attention attention_mma rowwise losses net graph; do
+for f in capi gemm_simt gemm_tc attention attention_mma rowwise losses head net graph; do
   nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr "$@" \
     -c "$csrc/$f.cu" -o "$obj/$f.o" &
   pids+=($!)
