@@ -70,6 +70,11 @@ int disc_head_fwd(const float* x, const float* w1, const float* b1, const float*
                   const float* b3, float* g0, float* f1, float* a1, float* f2, float* a2, float* out, int T, int d, float p_drop,
                   Seed seed, int site0, cudaStream_t st);
 
+int disc_head_bwd(const float* d_out, const float* out, const float* x, const float* g0, const float* f1, const float* a1,
+                  const float* f2, const float* a2, const float* w1, const float* w2, const float* w3, float* dx, float* dw1,
+                  float* db1, float* dw2, float* db2, float* dw3, float* db3, int T, int d, float p_drop, Seed seed, int site0,
+                  cudaStream_t st);
+
 // net.cu
 struct NetDims {
   int kind, S, B, d_in, d, nhead, dff, L, h1, h2;

@@ -309,6 +309,13 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
   const float* last_x2 = stash + sl.layer0 + (int64_t)(nd.L - 1) * sl.per_layer + sl.x2;
 
   // ---- head ----
+  if (!gen && !g_deterministic && disc_head_fusable(d, nd.h1, nd.h2)) {
+    // the whole discriminator head backward in one kernel (head.cu); its gradients accumulate with red.global.add, so
+    // the deterministic mode keeps the sequence of launches below
+    GANFFN_TRY(disc_head_bwd(d_out, out, last_x2, stash + sl.g0, stash + sl.f1, stash + sl.a1, stash + sl.f2, stash + sl.a2,
+                             P(hoff[FC1_W]), P(hoff[FC2_W]), P(hoff[FC3_W]), da, G(hoff[FC1_W]), G(hoff[FC1_B]), G(hoff[FC2_W]),
+                             G(hoff[FC2_B]), G(hoff[FC3_W]), G(hoff[FC3_B]), T, d, p_hd, seed, GANFFN_SITE_HEAD, st));
+  } else {
   if (gen) {
     // out = gelu(f2), f2 = drop(fc2(a1))
     GANFFN_TRY(elementwise(d_out, stash + sl.f2, hb2, (int64_t)T * nd.h2, EW_DGELU_MASK, p_hd, seed, GANFFN_SITE_HEAD + 2, st));
@@ -331,6 +338,7 @@ int net_bwd(const NetDims& nd, const float* params, const int64_t* off, const fl
     Epilogue ep; ep.dact = DACT_GELU; ep.dact_src = last_x2; ep.p_drop = gen ? p_hd : 0.f; ep.seed = seed;
     ep.site = GANFFN_SITE_HEAD + 0;
     GANFFN_TRY(cx.dgrad(hb1, P(hoff[FC1_W]), da, T, nd.h1, d, ep));
+  }
   }
 
   // ---- encoder layers, last to first ----
