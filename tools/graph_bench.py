@@ -108,6 +108,32 @@ def graph_leg(utterances=1_000_000, d=100, wp=10, wf=10, reps=5, device="cuda"):
                                  "GBps": (2 * (N * d * 4 + N * h * 4) + 2 * (E * 8 + N * 8 + N * R * 4)) / ms / 1e6}
     del rg, gc, xg
 
+    # ---- IEMOCAP-shaped batch (BASELINE config 2: "... + graph conv fwd/bwd"): the bench step's 32 dialogues x 94 turns, window
+    # 10/10, two speakers, fused features of width 100 -> DialogueGCN's RGCNConv then GraphConv (100 -> 100 -> 100), forward
+    # and backward, graph construction and pack / unpack included.  Launch-latency bound at this size (3 008 nodes).
+    S2, B2 = 94, 32
+    feats = torch.rand(S2, B2, d, device=dev, requires_grad=True)
+    spk2 = torch.randint(0, 2, (S2, B2), device=dev)
+    rg2, gc2 = RGCNConv(d, h, R).to(dev), GraphConv(h, h).to(dev)
+
+    def iemocap_step():
+        g2 = DialogueGraph([S2] * B2, spk2, wp, wf, 2, device=dev)
+        xn = g2.pack(feats)
+        y = gc2(torch.relu(rg2(xn, g2)), g2)
+        out_sbd = g2.unpack(y)
+        out_sbd.sum().backward()
+        feats.grad = None
+        for q in list(rg2.parameters()) + list(gc2.parameters()):
+            q.grad = None
+        return g2
+    g2 = iemocap_step()
+    ms = timed(iemocap_step)
+    out["iemocap_batch_build_rgcn_graphconv_fwd_bwd"] = {
+        "ms": ms, "nodes": g2.N, "edges": g2.E, "utterances_per_s": g2.N / ms * 1e3,
+        "what": "graph build (CSR + transposed CSR + edge_index) + pack + RGCNConv + ReLU + GraphConv + unpack, forward and backward, "
+                "eager launches, 32 dialogues x 94 turns (the bench step's batch)"}
+    del rg2, gc2, feats
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
