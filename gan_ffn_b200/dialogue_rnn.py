@@ -21,6 +21,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+_SIDE_STREAMS = {}   # device index -> side stream of BiModel.forward (module level: modules must stay picklable)
+
+
 class SimpleAttention(nn.Module):
     """reference model.py:22-37: softmax over time of a learned scalar score, weighted sum of the memory."""
 
@@ -195,13 +198,38 @@ class BiModel(nn.Module):
         return X.gather(0, idx) * valid.unsqueeze(2).to(X.dtype)
 
     def forward(self, U, qmask, umask, att2=True, max_len=None):
+        # The two directions are independent until the concatenation: on a CUDA device the reverse direction runs on
+        # a side stream (fork / join by events, so it is recordable into a CUDA graph; autograd replays each backward
+        # op on its forward stream, so the two backward recurrences overlap as well).  Every time step is a chain of
+        # small dependent kernels, so one direction alone leaves the device mostly idle.
+        side = None
+        if U.is_cuda and max_len is not None:
+            side = _SIDE_STREAMS.get(U.device.index)
+            if side is None:
+                side = torch.cuda.Stream(device=U.device)
+                _SIDE_STREAMS[U.device.index] = side
+            main = torch.cuda.current_stream(U.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rev_U = self._reverse_seq(U, umask, max_len)
+                rev_qmask = self._reverse_seq(qmask, umask, max_len)
+                emotions_b, alpha_b = self.dialog_rnn_r(rev_U, rev_qmask)
+                emotions_b = self._reverse_seq(emotions_b, umask, max_len)
+                emotions_b = self.dropout_rec(emotions_b)
         emotions_f, alpha_f = self.dialog_rnn_f(U, qmask)
         emotions_f = self.dropout_rec(emotions_f)
-        rev_U = self._reverse_seq(U, umask, max_len)
-        rev_qmask = self._reverse_seq(qmask, umask, max_len)
-        emotions_b, alpha_b = self.dialog_rnn_r(rev_U, rev_qmask)
-        emotions_b = self._reverse_seq(emotions_b, umask, max_len)
-        emotions_b = self.dropout_rec(emotions_b)
+        if side is not None:
+            main.wait_stream(side)
+            for tns in (U, qmask, umask):
+                tns.record_stream(side)          # allocated on the caller's stream, read on the side stream
+            for tns in [emotions_b] + [a for a in alpha_b if torch.is_tensor(a)]:
+                tns.record_stream(main)          # allocated on the side stream, read on the caller's
+        else:
+            rev_U = self._reverse_seq(U, umask, max_len)
+            rev_qmask = self._reverse_seq(qmask, umask, max_len)
+            emotions_b, alpha_b = self.dialog_rnn_r(rev_U, rev_qmask)
+            emotions_b = self._reverse_seq(emotions_b, umask, max_len)
+            emotions_b = self.dropout_rec(emotions_b)
         emotions = torch.cat([emotions_f, emotions_b], dim=-1)
         if att2:
             att_emotions, a = self.matchatt.all_steps(emotions, umask)
