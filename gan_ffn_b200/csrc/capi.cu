@@ -203,6 +203,22 @@ int ganffn_linear_ln_fwd(const float* x, const float* w, const float* bias, cons
   return gemm(x, K, false, w, K, true, z, N, M, N, K, ep, scratch, scratch_floats, S(stream));
 }
 
+int ganffn_disc_head_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                         const float* b3, float* g0, float* f1, float* a1, float* f2, float* a2, float* prob, int T, int d,
+                         float p_drop, uint64_t seed, int site0, void* stream) {
+  GANFFN_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && T >= 1, "disc_head_fwd: T=%d p=%f", T, p_drop);
+  return disc_head_fwd(x, w1, b1, w2, b2, w3, b3, g0, f1, a1, f2, a2, prob, T, d, p_drop, Seed(seed), site0, S(stream));
+}
+
+int ganffn_disc_head_bwd(const float* d_prob, const float* prob, const float* x, const float* g0, const float* f1, const float* a1,
+                         const float* f2, const float* a2, const float* w1, const float* w2, const float* w3, float* dx,
+                         float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3, int T, int d, float p_drop,
+                         uint64_t seed, int site0, void* stream) {
+  GANFFN_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && T >= 1, "disc_head_bwd: T=%d p=%f", T, p_drop);
+  return disc_head_bwd(d_prob, prob, x, g0, f1, a1, f2, a2, w1, w2, w3, dx, dw1, db1, dw2, db2, dw3, db3, T, d, p_drop, Seed(seed),
+                       site0, S(stream));
+}
+
 int ganffn_linear_dgrad(const float* dy, const float* w, const float* residual, float* dx, int M, int N, int K,
                         float* scratch, int64_t scratch_floats, void* stream) {
   GANFFN_CHECK_ARG(dy && w && dx, "linear_dgrad: null pointer");

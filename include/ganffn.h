@@ -112,6 +112,18 @@ int ganffn_linear_ln_fwd(const float* x, const float* w, const float* bias, cons
                          const float* gamma, const float* beta, float* z, float* y, int M, int N, int K,
                          float p_drop, uint64_t seed, int site, float* scratch, int64_t scratch_floats,
                          void* stream);
+/* The discriminator head (model.py:1320-1327, 1354-1364, 1390-1397) as one kernel each way:
+ *   g0 = gelu(x);  f1 = drop(fc1 g0) [64];  a1 = gelu(f1);  f2 = drop(fc2 a1) [16];  a2 = gelu(f2);  prob = sigmoid(drop(fc3 a2))
+ * x [T,d] (d <= 128, multiple of 4) is the last encoder output; w1 [64,d], w2 [16,64], w3 [16]; g0, f1, a1, f2, a2 are the
+ * intermediates the backward pass reads.  Dropout sites `site0 + 1..3` (fc1, fc2, fc3), masks = ganffn_dropout_mask.
+ * Backward: dx [T,d]; dw1 .. db3 are ACCUMULATED into (red.global.add); pass all six as NULL for a frozen network. */
+int ganffn_disc_head_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                         const float* w3, const float* b3, float* g0, float* f1, float* a1, float* f2, float* a2,
+                         float* prob, int T, int d, float p_drop, uint64_t seed, int site0, void* stream);
+int ganffn_disc_head_bwd(const float* d_prob, const float* prob, const float* x, const float* g0, const float* f1,
+                         const float* a1, const float* f2, const float* a2, const float* w1, const float* w2,
+                         const float* w3, float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3,
+                         float* db3, int T, int d, float p_drop, uint64_t seed, int site0, void* stream);
 /* Split-K workspace (floats) the GEMM engines want for an [M,N,K] product; may be 0. */
 int64_t ganffn_gemm_scratch_floats(int M, int N, int K);
 

@@ -129,6 +129,52 @@ def test_linear_layernorm_tail(L, engine, M, N, K, p):
     close(y, yr, f"LayerNorm output {M}x{N}x{K}", floor=2e-6)
 
 
+@pytest.mark.parametrize("T,d,p", [(3008, 100, 0.2), (6016, 100, 0.0), (130, 100, 0.2), (31, 64, 0.2), (1, 128, 0.0), (257, 100, 0.2)])
+def test_discriminator_head_kernels(L, T, d, p):
+    """gelu -> fc1 (d->64) -> fc2 (64->16) -> fc3 (16->1) -> sigmoid with dropout before each activation, forward and
+    backward in one kernel each (csrc/head.cu; reference model.py:1320-1327), against an fp64 restatement with the
+    exported masks; frozen variant (no parameter gradients) gives the same dx."""
+    from gan_ffn_b200.functional import dropout_mask
+    g = torch.Generator().manual_seed(T + d)
+    x = torch.randn(T, d, generator=g)
+    w1, b1 = torch.randn(64, d, generator=g) / math.sqrt(d), torch.randn(64, generator=g) * 0.1
+    w2, b2 = torch.randn(16, 64, generator=g) / 8, torch.randn(16, generator=g) * 0.1
+    w3, b3 = torch.randn(16, generator=g) / 4, torch.randn(1, generator=g) * 0.1
+    dp = torch.randn(T, generator=g)
+    seed, site0 = 0x5EEDF00D, 200
+    dv = [dev(t) for t in (x, w1, b1, w2, b2, w3, b3, dp)]
+    xd, w1d, b1d, w2d, b2d, w3d, b3d, dpd = dv
+    e = lambda *sh: torch.empty(*sh, device="cuda")
+    g0, f1, a1, f2, a2, prob = e(T, d), e(T, 64), e(T, 64), e(T, 16), e(T, 16), e(T)
+    L.call("ganffn_disc_head_fwd", P(xd), P(w1d), P(b1d), P(w2d), P(b2d), P(w3d), P(b3d), P(g0), P(f1), P(a1), P(f2), P(a2), P(prob),
+           T, d, p, seed, site0, stream())
+    m1 = dropout_mask(T, 64, p, seed, site0 + 1).double().cpu()
+    m2 = dropout_mask(T, 16, p, seed, site0 + 2).double().cpu()
+    m3 = dropout_mask(T, 1, p, seed, site0 + 3).double().cpu().view(-1)
+    X = x.double().requires_grad_(True)
+    W1, B1, W2, B2, W3, B3 = (t.double().requires_grad_(True) for t in (w1, b1, w2, b2, w3, b3))
+    G0 = O.gelu(X)
+    F1 = (G0 @ W1.T + B1) * m1
+    A1 = O.gelu(F1)
+    F2 = (A1 @ W2.T + B2) * m2
+    A2 = O.gelu(F2)
+    PR = torch.sigmoid((A2 @ W3 + B3) * m3)
+    for got, ref, name in ((g0, G0, "g0"), (f1, F1, "f1"), (a1, A1, "a1"), (f2, F2, "f2"), (a2, A2, "a2"), (prob, PR, "prob")):
+        close(got, ref, f"head {name}", floor=2e-6)
+    (PR * dp.double()).sum().backward()
+    grads = [torch.zeros_like(t) for t in (w1d, b1d, w2d, b2d, w3d, b3d)]
+    dx = e(T, d)
+    L.call("ganffn_disc_head_bwd", P(dpd), P(prob), P(xd), P(g0), P(f1), P(a1), P(f2), P(a2), P(w1d), P(w2d), P(w3d), P(dx),
+           *[P(t) for t in grads], T, d, p, seed, site0, stream())
+    close(dx, X.grad, "head dx", floor=5e-6)
+    for got, ref, name in zip(grads, (W1, B1, W2, B2, W3, B3), ("dw1", "db1", "dw2", "db2", "dw3", "db3")):
+        close(got, ref.grad.reshape(got.shape), f"head {name}", floor=5e-6)
+    dx2 = e(T, d)
+    L.call("ganffn_disc_head_bwd", P(dpd), P(prob), P(xd), None, P(f1), None, P(f2), None, P(w1d), P(w2d), P(w3d), P(dx2),
+           None, None, None, None, None, None, T, d, p, seed, site0, stream())
+    assert torch.equal(dx, dx2), "the frozen variant must give the same data gradient"
+
+
 def test_dropout_mask_statistics_and_determinism(L):
     from gan_ffn_b200.functional import dropout_mask
     for p in (0.1, 0.2, 0.6):
