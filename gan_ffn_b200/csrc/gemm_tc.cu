@@ -162,6 +162,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+// hi / lo split of two values at once: hi = rna_tf32(x) (two integer instructions each), lo = x - hi as ONE packed FFMA2
+// (fma(hi, -1, x) is exact: x - hi is representable).  The producers share their schedulers with the MMA-issuing thread,
+// so every instruction they do not issue shortens the main loop (§3.6 of DESIGN.md).
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
+  h0 = tf32_rna(x0);
+  h1 = tf32_rna(x1);
+  const float2 lo = __ffma2_rn(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.0f, -1.0f), make_float2(x0, x1));
+  l0 = __float_as_uint(lo.x);
+  l1 = __float_as_uint(lo.y);
+}
+
 // A operand from tensor memory (".ts"): lanes = rows of the tile, one tf32 per 32-bit column.
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -236,10 +247,7 @@ template <bool KMAJ>
 __device__ __forceinline__ void store_a(const float (&v)[16], uint32_t taddr, int x1 = 0) {
   uint32_t h[16], l[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    h[j] = tf32_rna(v[j]);
-    l[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
-  }
+  for (int j = 0; j < 16; j += 2) split2(v[j], v[j + 1], h[j], h[j + 1], l[j], l[j + 1]);
   if (KMAJ) {
     tmem_st_16x256b_x2(taddr, h);
     tmem_st_16x256b_x2(taddr + (16u << 16), h + 8);
@@ -283,11 +291,8 @@ __device__ __forceinline__ void store_b(const float4 (&v)[BCH], uint32_t hi, uin
   for (int i = 0; i < BCH; ++i) {
     const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
     uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = tf32_rna(x[j]);
-      l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));   // truncated by the tensor core (see store_a)
-    }
+    split2(x[0], x[1], h[0], h[1], l[0], l[1]);   // lo is truncated by the tensor core (see store_a)
+    split2(x[2], x[3], h[2], h[3], l[2], l[3]);
     sts128(hi + i * 4096, h[0], h[1], h[2], h[3]);
     if (!x1) sts128(lo + i * 4096, l[0], l[1], l[2], l[3]);
   }
@@ -938,11 +943,8 @@ __global__ void __launch_bounds__(A_NTHREADS, 1) gemm_tc_astat_kernel(const TcPa
           for (int i = 0; i < 4; ++i) {
             const float x[4] = {v[kb][i].x, v[kb][i].y, v[kb][i].z, v[kb][i].w};
             uint32_t h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              h[j] = tf32_rna(x[j]);
-              l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));
-            }
+            split2(x[0], x[1], h[0], h[1], l[0], l[1]);
+            split2(x[2], x[3], h[2], h[3], l[2], l[3]);
             sts128(hi + i * 2048, h[0], h[1], h[2], h[3]);
             if (!p.x1) sts128(hi + AB_TILE + i * 2048, l[0], l[1], l[2], l[3]);
           }
