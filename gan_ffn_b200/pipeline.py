@@ -8,7 +8,7 @@ padded batch to the GPU (train_IEMOCAP.py:137-140) and -- in stage 1 -- casts it
 stream one batch ahead of the compute stream (``DevicePrefetcher``), and padded on the device
 (``collate_on_device``: ``ganffn_graph_unpack`` for the three feature tensors, ``ganffn_collate_meta`` for
 ``qmask`` / ``umask`` / ``label``).  The result is the loader's batch bit for bit (``tests/test_pipeline.py`` compares
-it with ``pad_sequence``); nothing goes back to the host.
+it with ``oracle/collate_oracle.py``, the ``pad_sequence`` restatement); nothing goes back to the host.
 """
 from __future__ import annotations
 
@@ -78,14 +78,6 @@ def pack_batch(batch: Batch, pin: bool = True) -> PackedBatch:
         items.append((batch.text[:n, b], batch.visual[:n, b], batch.acoustic[:n, b], batch.qmask[:n, b], batch.umask[b, :n],
                       batch.label[b, :n]))
     return pack_dialogues(items, pin=pin)
-
-
-def collate_reference(items: Sequence[Sequence[torch.Tensor]]) -> Batch:
-    """CPU restatement of the reference's ``collate_fn`` (dataloader.py:55-58) for the six tensors of a batch --
-    test infrastructure for ``collate_on_device``."""
-    from torch.nn.utils.rnn import pad_sequence
-    cols = [pad_sequence([it[k] for it in items]) if k < 4 else pad_sequence([it[k] for it in items], True) for k in range(6)]
-    return Batch(cols[0], cols[1], cols[2], cols[3], cols[4], cols[5], [int(it[0].shape[0]) for it in items])
 
 
 def collate_on_device(pb: PackedBatch, seq_len: Optional[int] = None, n_speakers: int = 2) -> Batch:

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from gan_ffn_b200 import pipeline, synthetic
+from oracle.collate_oracle import collate_reference
 
 
 def _items(lengths, seed=0, n_classes=6):
@@ -24,7 +25,7 @@ def test_pack_is_the_inverse_of_the_reference_collate(lengths):
     assert pb.lengths_host == lengths and pb.seq_len == max(lengths) and pb.n_dialogues == len(lengths)
     assert pb.node_off.tolist() == [sum(lengths[:i]) for i in range(len(lengths) + 1)]
     assert pb.text.shape == (sum(lengths), 100) and pb.visual.shape == (sum(lengths), 512)
-    ref = pipeline.collate_reference(items)
+    ref = collate_reference(items)
     back = pipeline.pack_batch(ref, pin=False)
     for a, b in zip(pb.tensors(), back.tensors()):
         assert torch.equal(a, b)
@@ -53,7 +54,7 @@ def _same(a: synthetic.Batch, b: synthetic.Batch):
 @pytest.mark.parametrize("lengths", [[5, 1, 9], [110], [3, 3, 3, 3], [1], [17, 94, 2, 40, 40], list(range(1, 33))])
 def test_device_collate_is_bit_exact(lengths):
     items = _items(lengths, seed=3 + len(lengths))
-    ref = pipeline.collate_reference(items)
+    ref = collate_reference(items)
     got = pipeline.collate_on_device(pipeline.pack_dialogues(items).to("cuda"))
     _same(got, ref)
     # a longer (global) pad length, as a data-parallel shard gets it
@@ -76,7 +77,7 @@ def test_prefetcher_yields_the_loader_batches_in_order_and_feeds_a_train_step():
     packed = [pipeline.pack_dialogues(it) for it in batches]
     seen = 0
     for k, got in enumerate(pipeline.DevicePrefetcher(packed, "cuda")):
-        _same(got, pipeline.collate_reference(batches[k]))
+        _same(got, collate_reference(batches[k]))
         seen += 1
     assert seen == len(batches)
     assert list(pipeline.DevicePrefetcher([], "cuda")) == []
